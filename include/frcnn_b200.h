@@ -1,0 +1,169 @@
+/* frcnn_b200 -- C ABI of the B200 (sm_100a) Faster R-CNN inference path.
+ *
+ * Drop-in boundary for endernewton/tf-faster-rcnn's `Network.test_image()` / `im_detect()` / `nms()`
+ * hot path.  The reference's only native interface on this path is
+ *     void _nms(int* keep_out, int* num_out, const float* boxes_host, int boxes_num,
+ *               int boxes_dim, float nms_overlap_thresh, int device_id);      (lib/nms/gpu_nms.hpp:1-2)
+ * reached through lib/nms/gpu_nms.pyx:16-31 and lib/model/nms_wrapper.py:15-23; everything else on the
+ * path is TensorFlow graph ops called from Python (lib/nets/network.py).  This header therefore exports
+ *   (1) frcnn_nms_host      -- argument-compatible superset of `_nms` (same order + `flags`),
+ *   (2) one entry point per device stage of the TEST-mode graph, so the Python host code that mirrors
+ *       lib/nets/*.py can enqueue the graph on a CUDA stream (and capture it into a CUDA graph).
+ *
+ * Conventions
+ *   - plain C types only; every function returns 0 on success or a negative frcnn_status; the message of
+ *     the last failure on the calling thread is read with frcnn_last_error().  Nothing is printed
+ *     (the reference's CUDA_CHECK prints and continues, lib/nms/nms_kernel.cu:12-19).
+ *   - pointers named *_dev are device pointers owned by the caller (PyTorch tensors' data_ptr());
+ *     `stream` is a cudaStream_t passed as void*; all device entry points are asynchronous on it.
+ *   - activations: NHWC fp32, dense.  conv weights: packed by frcnn_pack_conv_weights.
+ *   - a handle/plan is single-stream and not re-entrant; one per GPU/rank.
+ */
+#ifndef FRCNN_B200_H_
+#define FRCNN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  FRCNN_OK = 0,
+  FRCNN_ERR_CUDA = -1,         /* a CUDA runtime/driver call failed (text in frcnn_last_error) */
+  FRCNN_ERR_ARG = -2,          /* invalid argument */
+  FRCNN_ERR_NO_DEVICE = -3,    /* no usable sm_100 device */
+  FRCNN_ERR_DRIVER_ENTRY = -4, /* cuTensorMapEncodeTiled not obtainable from the driver */
+  FRCNN_ERR_CAPACITY = -5      /* problem larger than the compiled-in capacity */
+} frcnn_status;
+
+/* NMS predicate flags. */
+#define FRCNN_NMS_PLUS_ONE 1u        /* '+1' pixel areas (cpu_nms.pyx / nms_kernel.cu); else continuous (TF) */
+#define FRCNN_NMS_INCLUSIVE 2u       /* suppress when ovr >= thr (cpu_nms.pyx:65); else ovr > thr */
+#define FRCNN_NMS_SKIP_DEGENERATE 4u /* IoU := 0 when either area <= 0 (tf.image.non_max_suppression) */
+#define FRCNN_NMS_MODE_CPU_NMS (FRCNN_NMS_PLUS_ONE | FRCNN_NMS_INCLUSIVE)
+#define FRCNN_NMS_MODE_GPU_NMS (FRCNN_NMS_PLUS_ONE)
+#define FRCNN_NMS_MODE_TF (FRCNN_NMS_SKIP_DEGENERATE)
+
+/* activation applied by conv/depthwise epilogues */
+#define FRCNN_ACT_NONE 0
+#define FRCNN_ACT_RELU 1
+#define FRCNN_ACT_RELU6 2
+
+int frcnn_version(void);
+/* copies the calling thread's last error text into buf (NUL terminated); returns its length */
+int frcnn_last_error(char* buf, size_t buflen);
+/* 0 when device `device_id` exists and is compute capability 10.x */
+int frcnn_check_device(int device_id);
+
+/* ---- (1) NMS, host buffers: replaces `_nms` (lib/nms/gpu_nms.hpp:1-2, nms_kernel.cu:91-144) ----------
+ * boxes_host: [boxes_num, boxes_dim>=4] rows (x1,y1,x2,y2,...), ALREADY sorted by descending score, as the
+ * reference's Cython wrapper guarantees (gpu_nms.pyx:25-28).  keep_out: capacity boxes_num; receives
+ * indices into the sorted input in ascending order.  Synchronous. */
+int frcnn_nms_host(int* keep_out, int* num_out, const float* boxes_host, int boxes_num, int boxes_dim,
+                   float nms_overlap_thresh, int device_id, unsigned flags);
+
+/* Same greedy NMS, device buffers, no sort: boxes_dev [n,4] in priority order.  keep_dev: capacity
+ * max_out (int32 indices into boxes_dev), num_dev: int32 count.  Early exit at max_out kept. */
+int frcnn_nms_sorted_dev(const float* boxes_dev, int n, float thresh, unsigned flags, int max_out,
+                         int* keep_dev, int* num_dev, void* stream);
+
+/* ---- (2) dense stages: conv / FC as implicit GEMM on tcgen05 (3xTF32, fp32 accumulate in TMEM) --------
+ * Replaces slim.conv2d / slim.fully_connected (+ folded bias or BatchNorm scale/shift, ReLU/ReLU6,
+ * residual add) as used by lib/nets/{vgg16,resnet_v1,mobilenet_v1}.py and network.py:323-378.
+ *   out[n,ho,wo,co] = act( (sum_{r,s,ci} in[n, ho*stride+r-pad_t, wo*stride+s-pad_l, ci] * w[co,r,s,ci])
+ *                          * scale[co] + shift[co] (+ residual[n,ho,wo,co]) )
+ * Requirements: cin % 32 == 0.  w_hi/w_lo from frcnn_pack_conv_weights.  scale may be NULL (=1). */
+typedef struct frcnn_conv_plan frcnn_conv_plan;
+
+typedef struct {
+  const float* in_dev;       /* [n, h, w, cin] */
+  const float* w_hi_dev;     /* [cout, kh*kw*cin] tf32-rounded weights */
+  const float* w_lo_dev;     /* [cout, kh*kw*cin] tf32-rounded residual w - w_hi */
+  const float* scale_dev;    /* [cout] or NULL */
+  const float* shift_dev;    /* [cout] or NULL */
+  const float* residual_dev; /* [n, ho, wo, cout] or NULL */
+  float* out_dev;            /* [n, ho, wo, cout] */
+  int n, h, w, cin;
+  int cout, kh, kw, stride;
+  int pad_t, pad_l;          /* zero padding before the first row / column */
+  int ho, wo;
+  int act;                   /* FRCNN_ACT_* */
+  int block_n;               /* 0 = choose; else 32/64/128 */
+} frcnn_conv_desc;
+
+int frcnn_conv_plan_create(frcnn_conv_plan** out, const frcnn_conv_desc* d);
+int frcnn_conv_plan_run(const frcnn_conv_plan* p, void* stream);
+int frcnn_conv_plan_info(const frcnn_conv_plan* p, int* block_n, int* tile_n, int* tile_h, int* tile_w,
+                         int* grid_m, int* grid_n, int* stages, int* smem_bytes);
+void frcnn_conv_plan_destroy(frcnn_conv_plan* p);
+
+/* HWIO [kh,kw,cin,cout] (TF layout) -> K-major [cout][kh][kw][cin], split into tf32 hi/lo planes. */
+int frcnn_pack_conv_weights(const float* w_hwio_dev, float* w_hi_dev, float* w_lo_dev, int kh, int kw,
+                            int cin, int cout, void* stream);
+
+/* ---- (3) bandwidth stages (SIMT, fp32, no FMA contraction where the oracle has separate roundings) ---- */
+/* first-layer convolution for cin==3 (vgg conv1_1, resnet conv1 7x7/2, mobilenet Conv2d_0 3x3/2):
+ * direct fp32 FFMA conv, w HWIO [k,k,3,cout], y = act(conv*scale + shift) */
+int frcnn_conv_first(const float* in_dev, const float* w_hwio_dev, const float* scale_dev,
+                     const float* shift_dev, float* out_dev, int n, int h, int w, int cout, int k,
+                     int stride, int pad_t, int pad_l, int ho, int wo, int act, void* stream);
+/* depthwise 3x3 (slim.separable_conv2d with num_outputs=None, mobilenet_v1.py:21-49):
+ * w [3,3,c] ; y = act(dw*scale + shift) */
+int frcnn_depthwise3x3(const float* in_dev, const float* w_dev, const float* scale_dev,
+                       const float* shift_dev, float* out_dev, int n, int h, int w, int c, int stride,
+                       int pad_t, int pad_l, int ho, int wo, int act, void* stream);
+/* max pool k x k / stride; padded cells are skipped when pad_is_neg_inf != 0 (TF 'SAME'),
+ * or count as zeros (tf.pad + 'VALID', resnet_v1.py:83-84) */
+int frcnn_max_pool(const float* in_dev, float* out_dev, int n, int h, int w, int c, int k, int stride,
+                   int pad_t, int pad_l, int ho, int wo, int pad_is_neg_inf, void* stream);
+/* mean over the spatial positions: [r, hw, c] -> [r, c]  (tf.reduce_mean axis=[1,2]) */
+int frcnn_spatial_mean(const float* in_dev, float* out_dev, int r, int hw, int c, void* stream);
+
+/* RPN: 2-way softmax (fg prob), anchor generation, bbox_transform_inv, clip -- proposal_layer.py:62-69.
+ * rpn_out_dev: [hw, ld] rows with the 2A class logits at column 0 and the 4A deltas at column delta_col
+ * (delta_col % 4 == 0, ld % 4 == 0: the fused 1x1 RPN head writes both).
+ * base_anchors_dev [A,4].  scores_dev [hw*A], props_dev [hw*A,4] in (h,w,a) order. */
+int frcnn_rpn_decode(const float* rpn_out_dev, int ld, int delta_col, const float* base_anchors_dev, int num_anchors,
+                     int fh, int fw, int feat_stride, float im_h, float im_w, float* scores_dev,
+                     float* props_dev, void* stream);
+/* stable descending sort of n fp32 keys (ties: lower index first) -> order_dev int32[n].
+ * workspace: frcnn_sort_workspace_bytes(n) bytes */
+size_t frcnn_sort_workspace_bytes(int n);
+int frcnn_sort_desc(const float* keys_dev, int n, int* order_dev, float* sorted_keys_dev, void* workspace_dev,
+                    size_t workspace_bytes, void* stream);
+/* proposal selection (proposal_layer_tf / proposal_layer / proposal_top_layer): walk `order`, greedy NMS
+ * with `flags` over the first `pre_nms_top_n` (<=0: all) candidates, stop at post_nms_top_n.  thresh < 0
+ * means no NMS (TEST.MODE='top').  rois_dev [post_nms_top_n,5] = (0,x1,y1,x2,y2), zero padded;
+ * roi_scores_dev [post_nms_top_n]; keep_dev int32 indices into props; num_dev int32 count. */
+int frcnn_proposals(const float* props_dev, const float* scores_dev, const int* order_dev, int n,
+                    int pre_nms_top_n, int post_nms_top_n, float thresh, unsigned flags, float* rois_dev,
+                    float* roi_scores_dev, int* keep_dev, int* num_dev, void* stream);
+/* tf.image.crop_and_resize on the stride-16 feature map + optional 2x2 max pool (network.py:141-157,
+ * resnet_v1.py:55-76).  rois_dev [r,5] blob-scale pixels.  pooled = 7; pre_pool 0: direct 7x7,
+ * 1: 14x14 then 2x2/2 max.  out [r,7,7,c] */
+int frcnn_crop_pool(const float* feat_dev, int fh, int fw, int c, const float* rois_dev, int r, int pooled,
+                    int pre_pool, float* out_dev, void* stream);
+/* split the fused [r, ld] head GEMM output (cls logits at col 0, 4C deltas at col C):
+ * cls_score [r,C], cls_prob = softmax, bbox_pred = delta*stds + means (network.py:361-378,428-432) */
+int frcnn_cls_finish(const float* head_out_dev, int ld, int r, int num_classes, const float* stds4,
+                     const float* means4, float* cls_score_dev, float* cls_prob_dev, float* bbox_pred_dev,
+                     void* stream);
+/* im_detect tail: boxes = rois[:,1:5]/scale; bbox_transform_inv; one-sided clip to the ORIGINAL image
+ * (lib/model/test.py:95-102,67-77).  pred_boxes_dev [r,4C] */
+int frcnn_bbox_decode(const float* rois_dev, const float* bbox_pred_dev, int r, int num_classes,
+                      float im_scale, int orig_h, int orig_w, float* pred_boxes_dev, void* stream);
+/* test_net tail (lib/model/test.py:162-180): per class j>=1: score > thresh, NMS(flags, nms_thresh), then the
+ * max_per_image cap over all classes.  num_rois_dev: int32 valid-row count (rows beyond are ignored).
+ * det_dev [max_det,6] = (x1,y1,x2,y2,score,class) sorted by (class, descending score); ndet_dev int32.
+ * keep_dev [C, r] int32 roi indices per class (after the cap), keep_cnt_dev [C]; keep_score_dev [C, r] scratch. */
+int frcnn_detect_post(const float* cls_prob_dev, const float* pred_boxes_dev, const int* num_rois_dev, int r,
+                      int num_classes, float score_thresh, float nms_thresh, unsigned flags,
+                      int max_per_image, int max_det, float* det_dev, int* ndet_dev, int* keep_dev,
+                      int* keep_cnt_dev, float* keep_score_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FRCNN_B200_H_ */

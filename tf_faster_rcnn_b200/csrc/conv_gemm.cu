@@ -1,0 +1,405 @@
+// Dense stages of the Faster R-CNN TEST graph as ONE implicit-GEMM kernel for sm_100a:
+//   slim.conv2d 3x3 / 1x1 (any stride), slim.fully_connected  (lib/nets/vgg16.py:26-60,
+//   resnet_v1 bottlenecks, mobilenet pointwise, lib/nets/network.py:323-378)
+//
+// Math: D[M=pixels, N=cout] = sum over (filter tap, cin chunk) A_tap[M, 32] * W[N, 32]^T, fp32-grade via the
+// 3xTF32 split  a*b ~= a_lo*b_hi + a_hi*b_lo + a_hi*b_hi  (hi = RN_tf32(x), lo = RN_tf32(x - hi)),
+// accumulated in fp32 in TMEM by tcgen05.mma.kind::tf32.
+//
+// Data movement: activations stay plain NHWC fp32 in HBM.  For filter tap (r,s) the A operand of a tile of
+// tn x th x tw output pixels is ONE 4-D TMA box {32 ch, tw, th, tn} of the input at offset
+// (w0*stride+s-pad_l, h0*stride+r-pad_t): out-of-bounds rows/cols are zero-filled by TMA, which IS the
+// convolution's zero padding -- no im2col buffer ever exists.  The box lands as <=128 rows x 128 B with
+// SWIZZLE_128B, exactly the K-major UMMA operand layout.  Weights are pre-split (hi/lo planes) and K-major.
+//
+// Warp roles (192 threads, 1 CTA/SM):
+//   warp 0      TMA producer            full[s]  <- tx bytes
+//   warps 2..5  operand splitter        wait full[s]; A -> (A_hi in place, A_lo) in smem; fence.proxy.async;
+//                                       arrive ready[s]           (elementwise => swizzle-agnostic)
+//   warp 1      MMA issuer (1 thread)   wait ready[s]; 4 k-slices x 3 tcgen05.mma; tcgen05.commit -> empty[s]
+//   warps 2..5  epilogue                wait tmem_full; tcgen05.ld; y = act(acc*scale + shift (+res)); st.global
+#include "common.cuh"
+#include "../../include/frcnn_b200.h"
+#include <stdlib.h>
+#include <string.h>
+
+namespace frcnn {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 32;                          // fp32 elements: 128 B = one swizzle row
+constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 4;  // 16 KiB
+constexpr int NUM_THREADS = 192;
+constexpr int SPLIT_THREADS = 128;
+
+struct ConvKernelParams {
+  float* out;
+  const float* residual;
+  const float* scale;
+  const float* shift;
+  int cout, ho, wo, nimg;
+  int tn, th, tw;
+  int tiles_h, tiles_w;
+  int kh, kw, cin, stride, pad_t, pad_l;
+  int act;
+  int a_box_bytes;
+};
+
+template <int BN> struct StageCfg;
+template <> struct StageCfg<128> { static constexpr int kStages = 3; };
+template <> struct StageCfg<64> { static constexpr int kStages = 4; };
+template <> struct StageCfg<32> { static constexpr int kStages = 5; };
+
+template <int BN> constexpr int stage_bytes() { return 2 * A_TILE_BYTES + 2 * BN * BLOCK_K * 4; }
+template <int BN> constexpr int smem_bytes() { return StageCfg<BN>::kStages * stage_bytes<BN>() + 1024 /*align slack*/ + 256 /*barriers*/; }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (8-row x 128 B atoms, 1024 B apart)
+__device__ __forceinline__ uint64_t sw128_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;                  // LBO: unused for swizzled K-major
+  d |= (uint64_t)(1024u >> 4) << 32;       // SBO
+  d |= (uint64_t)1 << 46;                  // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                  // SWIZZLE_128B
+  return d;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
+                        const __grid_constant__ CUtensorMap tmBlo, const ConvKernelParams p) {
+  constexpr int kStages = StageCfg<BN>::kStages;
+  constexpr int kStageBytes = stage_bytes<BN>();
+  constexpr int kBTile = BN * BLOCK_K * 4;
+  constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint64_t* ready = full + kStages;
+  uint64_t* empty = ready + kStages;
+  uint64_t* tmem_full = empty + kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // tile coordinates
+  const int mt = blockIdx.x;
+  const int tile_w = mt % p.tiles_w;
+  const int tile_h = (mt / p.tiles_w) % p.tiles_h;
+  const int tile_n = mt / (p.tiles_w * p.tiles_h);
+  const int w0 = tile_w * p.tw, h0 = tile_h * p.th, n0 = tile_n * p.tn;
+  const int nblk = blockIdx.y;
+  const int num_kb = p.kh * p.kw * (p.cin / BLOCK_K);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmBhi); tma_prefetch_desc(&tmBlo);
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&ready[s], SPLIT_THREADS); mbar_init(&empty[s], 1); }
+    mbar_init(tmem_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, BN); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      const int cchunks = p.cin / BLOCK_K;
+      for (int r = 0; r < p.kh; ++r)
+        for (int s = 0; s < p.kw; ++s)
+          for (int kc = 0; kc < cchunks; ++kc) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            uint8_t* st = smem + stage * kStageBytes;
+            mbar_expect_tx(&full[stage], (uint32_t)(p.a_box_bytes + 2 * kBTile));
+            tma_load_4d(st, &tmA, &full[stage], kc * BLOCK_K, w0 * p.stride + s - p.pad_l, h0 * p.stride + r - p.pad_t, n0);
+            const int kcoord = ((r * p.kw + s) * p.cin) + kc * BLOCK_K;
+            tma_load_2d(st + 2 * A_TILE_BYTES, &tmBhi, &full[stage], kcoord, nblk * BN);
+            tma_load_2d(st + 2 * A_TILE_BYTES + kBTile, &tmBlo, &full[stage], kcoord, nblk * BN);
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&ready[stage], phase);
+        tc_fence_after();
+        const uint32_t sbase = smem_u32(smem + stage * kStageBytes);
+        const uint64_t a_hi = sw128_desc(sbase);
+        const uint64_t a_lo = sw128_desc(sbase + A_TILE_BYTES);
+        const uint64_t b_hi = sw128_desc(sbase + 2 * A_TILE_BYTES);
+        const uint64_t b_lo = sw128_desc(sbase + 2 * A_TILE_BYTES + kBTile);
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / 8; ++k) {
+          const uint64_t off = (uint64_t)(k * 8 * 4) >> 4;   // advance 8 tf32 = 32 B inside the swizzle row
+          umma_tf32(tmem_base, a_lo + off, b_hi + off, kIdesc, (kb > 0 || k > 0) ? 1u : 0u);
+          umma_tf32(tmem_base, a_hi + off, b_lo + off, kIdesc, 1u);
+          umma_tf32(tmem_base, a_hi + off, b_hi + off, kIdesc, 1u);
+        }
+        umma_commit(&empty[stage]);
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(tmem_full);
+    }
+    __syncwarp();
+  } else {
+    // ---------------- operand splitter ----------------
+    const int t = threadIdx.x - 64;
+    {
+      int stage = 0; uint32_t phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full[stage], phase);
+        float4* a = reinterpret_cast<float4*>(smem + stage * kStageBytes);
+        float4* alo = reinterpret_cast<float4*>(smem + stage * kStageBytes + A_TILE_BYTES);
+#pragma unroll
+        for (int i = 0; i < A_TILE_BYTES / 16 / SPLIT_THREADS; ++i) {
+          const int idx = i * SPLIT_THREADS + t;
+          float4 v = a[idx], h, l;
+          h.x = to_tf32(v.x); h.y = to_tf32(v.y); h.z = to_tf32(v.z); h.w = to_tf32(v.w);
+          l.x = to_tf32(__fsub_rn(v.x, h.x)); l.y = to_tf32(__fsub_rn(v.y, h.y));
+          l.z = to_tf32(__fsub_rn(v.z, h.z)); l.w = to_tf32(__fsub_rn(v.w, h.w));
+          a[idx] = h; alo[idx] = l;
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(&ready[stage]);
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+    // ---------------- epilogue ----------------
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;
+    const int rows_img = p.th * p.tw;
+    const int dn = row / rows_img, rem = row % rows_img;
+    const int dh = rem / p.tw, dw = rem % p.tw;
+    const int n = n0 + dn, h = h0 + dh, w = w0 + dw;
+    const bool valid = (row < p.tn * rows_img) && n < p.nimg && h < p.ho && w < p.wo;
+    const size_t pix = valid ? (((size_t)n * p.ho + h) * p.wo + w) : 0;
+    float* orow = p.out + pix * p.cout;
+    const float* rrow = p.residual ? p.residual + pix * p.cout : nullptr;
+    const bool vec_ok = (p.cout & 3) == 0;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      const int cbase = nblk * BN + c0;
+      if (cbase >= p.cout) break;
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      tmem_ld_wait();
+      if (valid) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const int c = cbase + j;
+          if (c >= p.cout) break;
+          float y[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float acc = __uint_as_float(v[j + e]);
+            const int ce = c + e;
+            if (ce < p.cout) {
+              if (p.scale) acc = __fmul_rn(acc, __ldg(p.scale + ce));
+              if (p.shift) acc = __fadd_rn(acc, __ldg(p.shift + ce));
+              if (rrow) acc = __fadd_rn(acc, __ldg(rrow + ce));
+              if (p.act == FRCNN_ACT_RELU) acc = fmaxf(acc, 0.f);
+              else if (p.act == FRCNN_ACT_RELU6) acc = fminf(fmaxf(acc, 0.f), 6.f);
+            }
+            y[e] = acc;
+          }
+          if (vec_ok) {
+            *reinterpret_cast<float4*>(orow + c) = make_float4(y[0], y[1], y[2], y[3]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) if (c + e < p.cout) orow[c + e] = y[e];
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, BN); }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+static int encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                      const uint32_t* box, const uint32_t* estr) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return ERR_DRIVER_ENTRY; }
+  cuuint64_t gd[5]; cuuint64_t gs[4]; cuuint32_t bx[5]; cuuint32_t es[5];
+  for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = estr[i]; }
+  for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (CUresult %d) rank=%d dims=[%llu,%llu,%llu,%llu] box=[%u,%u,%u,%u]", (int)r, rank,
+              (unsigned long long)dims[0], (unsigned long long)dims[1], rank > 2 ? (unsigned long long)dims[2] : 0ull,
+              rank > 3 ? (unsigned long long)dims[3] : 0ull, box[0], box[1], rank > 2 ? box[2] : 0u, rank > 3 ? box[3] : 0u);
+    return ERR_CUDA;
+  }
+  return OK;
+}
+
+}  // namespace frcnn
+
+using namespace frcnn;
+
+struct frcnn_conv_plan {
+  CUtensorMap tmA, tmBhi, tmBlo;
+  ConvKernelParams kp;
+  int block_n, stages, smem;
+  dim3 grid;
+};
+
+// choose the tile of output pixels (tn x th x tw <= 128) that needs the fewest tiles
+static void choose_tile(int n, int ho, int wo, int stride, int* tn, int* th, int* tw) {
+  long best_tiles = -1; int bn = 1, bh = 1, bw = 1; int best_rows = 0;
+  const int lim = 256 / stride;
+  for (int a = 1; a <= n && a <= BLOCK_M; ++a)
+    for (int b = 1; b <= ho && a * b <= BLOCK_M && b <= lim; ++b) {
+      int c = BLOCK_M / (a * b);
+      if (c > wo) c = wo;
+      if (c > lim) c = lim;
+      if (c < 1) continue;
+      // shrink c to the smallest width giving the same tile count (less garbage rows)
+      int tiles_w = cdiv(wo, c);
+      c = cdiv(wo, tiles_w);
+      long tiles = (long)cdiv(n, a) * cdiv(ho, b) * tiles_w;
+      int rows = a * b * c;
+      if (best_tiles < 0 || tiles < best_tiles || (tiles == best_tiles && rows < best_rows)) {
+        best_tiles = tiles; bn = a; bh = b; bw = c; best_rows = rows;
+      }
+    }
+  *tn = bn; *th = bh; *tw = bw;
+}
+
+template <int BN>
+static int launch(const frcnn_conv_plan* p, cudaStream_t st) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    FRCNN_CUDA(cudaFuncSetAttribute(conv_gemm_tf32x3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<BN>()));
+    attr_done = true;
+  }
+  conv_gemm_tf32x3_kernel<BN><<<p->grid, NUM_THREADS, smem_bytes<BN>(), st>>>(p->tmA, p->tmBhi, p->tmBlo, p->kp);
+  FRCNN_LAUNCH_CHECK();
+  return OK;
+}
+
+extern "C" int frcnn_conv_plan_create(frcnn_conv_plan** out, const frcnn_conv_desc* d) {
+  FRCNN_REQUIRE(out && d, "null argument");
+  FRCNN_REQUIRE(d->cin > 0 && d->cin % BLOCK_K == 0, "cin=%d must be a positive multiple of 32", d->cin);
+  FRCNN_REQUIRE(d->kh >= 1 && d->kw >= 1 && d->stride >= 1 && d->stride <= 8, "bad filter geometry");
+  FRCNN_REQUIRE(d->in_dev && d->w_hi_dev && d->w_lo_dev && d->out_dev, "null device pointer");
+  FRCNN_REQUIRE(d->n > 0 && d->h > 0 && d->w > 0 && d->ho > 0 && d->wo > 0 && d->cout > 0, "bad shape");
+  frcnn_conv_plan* p = (frcnn_conv_plan*)aligned_alloc(64, (sizeof(frcnn_conv_plan) + 63) / 64 * 64);
+  if (!p) { set_error("out of host memory"); return ERR_ARG; }
+  memset(p, 0, sizeof(*p));
+
+  int n = d->n, h = d->h, w = d->w, ho = d->ho, wo = d->wo;
+  const bool pointwise = d->kh == 1 && d->kw == 1 && d->stride == 1 && d->pad_t == 0 && d->pad_l == 0 && ho == h && wo == w;
+  if (pointwise) {  // flatten all pixels into one row of "width" n*h*w: perfect 128-row tiles
+    w = wo = n * h * w; n = 1; h = ho = 1;
+  }
+  int tn, th, tw;
+  choose_tile(n, ho, wo, d->stride, &tn, &th, &tw);
+  const int tiles_w = cdiv(wo, tw), tiles_h = cdiv(ho, th), tiles_n = cdiv(n, tn);
+  const long m_tiles = (long)tiles_w * tiles_h * tiles_n;
+  const int num_kb = d->kh * d->kw * d->cin / BLOCK_K;
+
+  int bn = d->block_n;
+  if (bn == 0) {
+    long best = -1;
+    const int cands[3] = {128, 64, 32};
+    for (int i = 0; i < 3; ++i) {
+      const int c = cands[i];
+      if (c > 32 && c / 2 >= d->cout) continue;        // tile mostly empty
+      const long ctas = m_tiles * cdiv(d->cout, c);
+      const long waves = (ctas + 147) / 148;
+      long per_kb = 6L * c; if (per_kb < 420) per_kb = 420;   // MMA cycles vs per-k-block floor (TMA/split/issue)
+      const long cost = waves * (num_kb * per_kb + 3000);
+      if (best < 0 || cost < best) { best = cost; bn = c; }
+    }
+  }
+  FRCNN_REQUIRE(bn == 32 || bn == 64 || bn == 128, "block_n must be 32, 64 or 128");
+
+  // A: NHWC activations as a rank-4 tensor {C, W, H, N}; traversal stride = conv stride on W and H
+  {
+    uint64_t dims[4] = {(uint64_t)d->cin, (uint64_t)w, (uint64_t)h, (uint64_t)n};
+    uint64_t strides[3] = {(uint64_t)d->cin * 4, (uint64_t)w * d->cin * 4, (uint64_t)h * w * d->cin * 4};
+    uint32_t box[4] = {(uint32_t)BLOCK_K, (uint32_t)(tw * d->stride), (uint32_t)(th * d->stride), (uint32_t)tn};
+    uint32_t es[4] = {1, (uint32_t)d->stride, (uint32_t)d->stride, 1};
+    int rc = encode_map(&p->tmA, d->in_dev, 4, dims, strides, box, es);
+    if (rc) { free(p); return rc; }
+  }
+  {
+    const uint64_t ktot = (uint64_t)d->kh * d->kw * d->cin;
+    uint64_t dims[2] = {ktot, (uint64_t)d->cout};
+    uint64_t strides[1] = {ktot * 4};
+    uint32_t box[2] = {(uint32_t)BLOCK_K, (uint32_t)bn};
+    uint32_t es[2] = {1, 1};
+    int rc = encode_map(&p->tmBhi, d->w_hi_dev, 2, dims, strides, box, es);
+    if (!rc) rc = encode_map(&p->tmBlo, d->w_lo_dev, 2, dims, strides, box, es);
+    if (rc) { free(p); return rc; }
+  }
+  ConvKernelParams& k = p->kp;
+  k.out = d->out_dev; k.residual = d->residual_dev; k.scale = d->scale_dev; k.shift = d->shift_dev;
+  k.cout = d->cout; k.ho = ho; k.wo = wo; k.nimg = n;
+  k.tn = tn; k.th = th; k.tw = tw; k.tiles_h = tiles_h; k.tiles_w = tiles_w;
+  k.kh = d->kh; k.kw = d->kw; k.cin = d->cin; k.stride = d->stride; k.pad_t = d->pad_t; k.pad_l = d->pad_l;
+  k.act = d->act;
+  k.a_box_bytes = tn * th * tw * BLOCK_K * 4;
+  p->block_n = bn;
+  p->stages = bn == 128 ? StageCfg<128>::kStages : bn == 64 ? StageCfg<64>::kStages : StageCfg<32>::kStages;
+  p->smem = bn == 128 ? smem_bytes<128>() : bn == 64 ? smem_bytes<64>() : smem_bytes<32>();
+  FRCNN_REQUIRE(m_tiles <= 0x7fffffffL, "too many tiles");
+  p->grid = dim3((unsigned)m_tiles, (unsigned)cdiv(d->cout, bn), 1);
+  *out = p;
+  return OK;
+}
+
+extern "C" int frcnn_conv_plan_run(const frcnn_conv_plan* p, void* stream) {
+  FRCNN_REQUIRE(p, "null plan");
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (p->block_n) {
+    case 128: return launch<128>(p, st);
+    case 64: return launch<64>(p, st);
+    default: return launch<32>(p, st);
+  }
+}
+
+extern "C" int frcnn_conv_plan_info(const frcnn_conv_plan* p, int* block_n, int* tile_n, int* tile_h, int* tile_w,
+                                    int* grid_m, int* grid_n, int* stages, int* smem) {
+  FRCNN_REQUIRE(p, "null plan");
+  if (block_n) *block_n = p->block_n;
+  if (tile_n) *tile_n = p->kp.tn;
+  if (tile_h) *tile_h = p->kp.th;
+  if (tile_w) *tile_w = p->kp.tw;
+  if (grid_m) *grid_m = (int)p->grid.x;
+  if (grid_n) *grid_n = (int)p->grid.y;
+  if (stages) *stages = p->stages;
+  if (smem) *smem = p->smem;
+  return OK;
+}
+
+extern "C" void frcnn_conv_plan_destroy(frcnn_conv_plan* p) { free(p); }

@@ -1,0 +1,463 @@
+// Both NMS passes of the TEST path + the score sort, for sm_100a.
+//   RPN stage   : proposal_layer_tf / proposal_layer / proposal_top_layer (lib/layer_utils/proposal_layer.py:16-83,
+//                 proposal_top_layer.py:58-85)                                   -> frcnn_proposals
+//   final stage : per-class NMS + max_per_image cap (lib/model/test.py:162-180) -> frcnn_detect_post
+//   `_nms` ABI  : lib/nms/gpu_nms.hpp:1-2                                        -> frcnn_nms_host
+//
+// Algorithm (replaces nms_kernel.cu's N x N/64 bitmask + host sweep, which is O(N^2) work and memory even
+// though at most post_nms_top_n boxes survive): candidates are walked in priority order in chunks of 256.
+// For one chunk the CTA (a) tests every candidate against the <=K boxes already kept (kept set lives in shared
+// memory), (b) builds the 256x256 intra-chunk suppression bitmask, (c) one thread resolves the chunk
+// sequentially with 4 x 64-bit words; survivors are appended to the kept set.  The walk stops as soon as
+// max_out boxes are kept, so the RPN stage touches only the first few thousand of the 17k-50k anchors.
+// IoU arithmetic is the oracle's op-by-op fp32 sequence (__f*_rn: no FMA contraction) for all three predicate
+// variants (flags), so survivor indices are bit-exact.
+#include "common.cuh"
+#include "../../include/frcnn_b200.h"
+#include <cub/device/device_radix_sort.cuh>
+
+namespace frcnn {
+
+constexpr int NMS_THREADS = 1024;
+constexpr int CHUNK = 256;
+
+__device__ __forceinline__ float box_area(const float4 b, unsigned flags) {
+  if (flags & FRCNN_NMS_PLUS_ONE) return __fmul_rn(__fadd_rn(__fsub_rn(b.z, b.x), 1.f), __fadd_rn(__fsub_rn(b.w, b.y), 1.f));
+  return __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
+}
+
+// TF normalises corners with min/max first (boxes are (y1,x1,y2,x2) there; the formula is symmetric in x/y)
+__device__ __forceinline__ float4 canon(const float4 b, unsigned flags) {
+  if (flags & FRCNN_NMS_PLUS_ONE) return b;
+  return make_float4(fminf(b.x, b.z), fminf(b.y, b.w), fmaxf(b.x, b.z), fmaxf(b.y, b.w));
+}
+
+__device__ __forceinline__ bool suppresses(const float4 a, float area_a, const float4 b, float area_b, float thr, unsigned flags) {
+  float inter;
+  if (flags & FRCNN_NMS_PLUS_ONE) {
+    const float w = fmaxf(0.f, __fadd_rn(__fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)), 1.f));
+    const float h = fmaxf(0.f, __fadd_rn(__fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)), 1.f));
+    inter = __fmul_rn(w, h);
+  } else {
+    if ((flags & FRCNN_NMS_SKIP_DEGENERATE) && (area_a <= 0.f || area_b <= 0.f)) return false;
+    const float h = fmaxf(__fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)), 0.f);
+    const float w = fmaxf(__fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)), 0.f);
+    inter = __fmul_rn(h, w);
+  }
+  const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter));
+  return (flags & FRCNN_NMS_INCLUSIVE) ? (ovr >= thr) : (ovr > thr);
+}
+
+struct GreedyShared {
+  unsigned long long mask[CHUNK][CHUNK / 64];
+  float4 cbox[CHUNK];
+  float carea[CHUNK];
+  int dead[CHUNK];
+  int nkept;
+  int chunk_kept[CHUNK];
+  int chunk_nk;
+};
+
+// CTA-cooperative greedy NMS over `m` candidates given in priority order.
+//   cand(i) -> float4 box of the i-th candidate;  kept/kept_area: storage for the kept set (shared or global)
+//   kept_pos: positions (0..m-1) of survivors.   returns number kept (in sh.nkept, valid after the final barrier)
+template <typename CandFn>
+__device__ void block_greedy_nms(CandFn cand, int m, float thr, unsigned flags, int max_out, float4* kept, float* kept_area,
+                                 int* kept_pos, GreedyShared& sh) {
+  const int tid = threadIdx.x;
+  if (tid == 0) sh.nkept = 0;
+  __syncthreads();
+  for (int base = 0; base < m; base += CHUNK) {
+    const int cn = min(CHUNK, m - base);
+    const int nk = sh.nkept;
+    if (nk >= max_out) break;
+    if (tid < CHUNK) {
+      sh.dead[tid] = 0;
+      if (tid < cn) {
+        const float4 b = canon(cand(base + tid), flags);
+        sh.cbox[tid] = b;
+        sh.carea[tid] = box_area(b, flags);
+      }
+    }
+    __syncthreads();
+    // (a) candidates vs kept set: 4 threads per candidate stride over the kept boxes
+    if (thr >= 0.f) {
+      const int c = tid >> 2, part = tid & 3;
+      if (c < cn) {
+        const float4 b = sh.cbox[c];
+        const float ab = sh.carea[c];
+        bool d = false;
+        for (int k = part; k < nk && !d; k += 4) d = suppresses(kept[k], kept_area[k], b, ab, thr, flags);
+        if (d) sh.dead[c] = 1;
+      }
+      // (b) intra-chunk bitmask: thread (row i, 64-bit word wj); only j > i matters
+      const int i = tid >> 2, wj = tid & 3;
+      if (i < cn) {
+        unsigned long long bits = 0ull;
+        const float4 a = sh.cbox[i];
+        const float aa = sh.carea[i];
+        const int j0 = wj * 64;
+        for (int j = max(j0, i + 1); j < min(j0 + 64, cn); ++j)
+          if (suppresses(a, aa, sh.cbox[j], sh.carea[j], thr, flags)) bits |= 1ull << (j - j0);
+        sh.mask[i][wj] = bits;
+      }
+    }
+    __syncthreads();
+    // (c) sequential resolve of the chunk
+    if (tid == 0) {
+      static_assert(CHUNK == 256, "resolve loop is written for 4 x 64-bit words");
+      unsigned long long r0 = 0ull, r1 = 0ull, r2 = 0ull, r3 = 0ull;
+      int k = nk, ck = 0;
+      for (int i = 0; i < cn && k < max_out; ++i) {
+        if (sh.dead[i]) continue;
+        const int w = i >> 6;
+        const unsigned long long cur = w == 0 ? r0 : w == 1 ? r1 : w == 2 ? r2 : r3;
+        if ((cur >> (i & 63)) & 1ull) continue;
+        sh.chunk_kept[ck++] = i;
+        ++k;
+        if (thr >= 0.f) { r0 |= sh.mask[i][0]; r1 |= sh.mask[i][1]; r2 |= sh.mask[i][2]; r3 |= sh.mask[i][3]; }
+      }
+      sh.chunk_nk = ck;
+    }
+    __syncthreads();
+    const int ck = sh.chunk_nk;
+    if (tid < ck) {
+      const int i = sh.chunk_kept[tid];
+      kept[nk + tid] = sh.cbox[i];
+      kept_area[nk + tid] = sh.carea[i];
+      kept_pos[nk + tid] = base + i;
+    }
+    __syncthreads();
+    if (tid == 0) sh.nkept = nk + ck;
+    __syncthreads();
+  }
+  __syncthreads();
+}
+
+// ---- RPN proposal selection ---------------------------------------------------------------------------
+constexpr int PROPOSAL_CAP = 1024;   // kept set held in shared memory (post_nms_top_n: 300 / 1000 / 'top' handled separately)
+
+__global__ void __launch_bounds__(NMS_THREADS, 1)
+proposals_kernel(const float4* __restrict__ props, const float* __restrict__ scores, const int* __restrict__ order, int m,
+                 int max_out, float thr, unsigned flags, float* __restrict__ rois, float* __restrict__ roi_scores,
+                 int* __restrict__ keep, int* __restrict__ num) {
+  __shared__ GreedyShared sh;
+  __shared__ float4 kept[PROPOSAL_CAP];
+  __shared__ float kept_area[PROPOSAL_CAP];
+  __shared__ int kept_pos[PROPOSAL_CAP];
+  block_greedy_nms([&](int i) { return __ldg(props + __ldg(order + i)); }, m, thr, flags, max_out, kept, kept_area, kept_pos, sh);
+  const int nk = sh.nkept;
+  for (int i = threadIdx.x; i < max_out; i += blockDim.x) {
+    float* r = rois + (size_t)i * 5;
+    if (i < nk) {
+      const int src = __ldg(order + kept_pos[i]);
+      const float4 b = __ldg(props + src);   // un-normalised original box
+      r[0] = 0.f; r[1] = b.x; r[2] = b.y; r[3] = b.z; r[4] = b.w;
+      roi_scores[i] = __ldg(scores + src);
+      keep[i] = src;
+    } else {
+      r[0] = r[1] = r[2] = r[3] = r[4] = 0.f;
+      roi_scores[i] = 0.f;
+      keep[i] = -1;
+    }
+  }
+  if (threadIdx.x == 0) *num = nk;
+}
+
+// 'top' mode (no NMS) with more outputs than the shared-memory kept set: plain gather of the first max_out
+__global__ void gather_top_kernel(const float4* __restrict__ props, const float* __restrict__ scores, const int* __restrict__ order,
+                                  int m, int max_out, float* __restrict__ rois, float* __restrict__ roi_scores,
+                                  int* __restrict__ keep, int* __restrict__ num) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) *num = min(m, max_out);
+  if (i >= max_out) return;
+  float* r = rois + (size_t)i * 5;
+  if (i < m) {
+    const int src = __ldg(order + i);
+    const float4 b = __ldg(props + src);
+    r[0] = 0.f; r[1] = b.x; r[2] = b.y; r[3] = b.z; r[4] = b.w;
+    roi_scores[i] = __ldg(scores + src);
+    keep[i] = src;
+  } else {
+    r[0] = r[1] = r[2] = r[3] = r[4] = 0.f;
+    roi_scores[i] = 0.f;
+    keep[i] = -1;
+  }
+}
+
+// ---- generic sorted-input NMS with the kept set in global memory (the `_nms` compatible path) -----------
+__global__ void __launch_bounds__(NMS_THREADS, 1)
+nms_sorted_kernel(const float* __restrict__ boxes, int stride, int m, float thr, unsigned flags, int max_out,
+                  float4* __restrict__ kept, float* __restrict__ kept_area, int* __restrict__ keep, int* __restrict__ num) {
+  __shared__ GreedyShared sh;
+  block_greedy_nms([&](int i) { const float* b = boxes + (size_t)i * stride; return make_float4(b[0], b[1], b[2], b[3]); }, m, thr,
+                   flags, max_out, kept, kept_area, keep, sh);
+  if (threadIdx.x == 0) *num = sh.nkept;
+}
+
+// ---- final per-class NMS + cap -----------------------------------------------------------------------------
+constexpr int DET_CAP = 1024;  // max RoIs per image handled by the per-class kernel (cfg 5 uses 1000)
+
+// one CTA per foreground class
+__global__ void __launch_bounds__(NMS_THREADS, 1)
+class_nms_kernel(const float* __restrict__ probs, const float4* __restrict__ pred, const int* __restrict__ num_rois, int r, int C,
+                 float score_thresh, float nms_thresh, unsigned flags, int* __restrict__ keep, int* __restrict__ keep_cnt,
+                 float* __restrict__ keep_score) {
+  __shared__ GreedyShared sh;
+  __shared__ float4 kept[DET_CAP];
+  __shared__ float kept_area[DET_CAP];
+  __shared__ int kept_pos[DET_CAP];
+  __shared__ float skey[DET_CAP];
+  __shared__ int sidx[DET_CAP];
+  __shared__ int s_m;
+  const int cls = blockIdx.x + 1;
+  const int tid = threadIdx.x;
+  const int nr = min(*num_rois, r);
+  // candidates: score > thresh (test.py:163); sort key (score desc, index asc); invalid -> -inf at the tail
+  if (tid == 0) s_m = 0;
+  __syncthreads();
+  {
+    float key = __int_as_float(0xff800000);
+    if (tid < nr) {
+      const float s = __ldg(probs + (size_t)tid * C + cls);
+      if (s > score_thresh) { key = s; atomicAdd(&s_m, 1); }
+    }
+    skey[tid] = key; sidx[tid] = tid;
+  }
+  __syncthreads();
+  // bitonic sort of 1024 (key desc, idx asc)
+  for (int k = 2; k <= DET_CAP; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      const int ixj = tid ^ j;
+      if (ixj > tid) {
+        const float a = skey[tid], b = skey[ixj];
+        const int ia = sidx[tid], ib = sidx[ixj];
+        const bool a_first = (a > b) || (a == b && ia < ib);   // a precedes b in the final order
+        const bool up = (tid & k) == 0;
+        if (up ? !a_first : a_first) { skey[tid] = b; skey[ixj] = a; sidx[tid] = ib; sidx[ixj] = ia; }
+      }
+      __syncthreads();
+    }
+  }
+  const int m = s_m;
+  block_greedy_nms([&](int i) { return __ldg(pred + (size_t)sidx[i] * C + cls); }, m, nms_thresh, flags, m, kept, kept_area, kept_pos, sh);
+  const int nk = sh.nkept;
+  for (int i = tid; i < r; i += blockDim.x) {
+    if (i < nk) { keep[(size_t)cls * r + i] = sidx[kept_pos[i]]; keep_score[(size_t)cls * r + i] = skey[kept_pos[i]]; }
+    else { keep[(size_t)cls * r + i] = -1; keep_score[(size_t)cls * r + i] = 0.f; }
+  }
+  if (tid == 0) keep_cnt[cls] = nk;
+  if (blockIdx.x == 0) {
+    for (int i = tid; i < r; i += blockDim.x) { keep[i] = -1; keep_score[i] = 0.f; }
+    if (tid == 0) keep_cnt[0] = 0;
+  }
+}
+
+// single CTA: k-th largest kept score by 4-pass radix select (scores > 0 => uint order == float order), then
+// filter (score >= image_thresh, ties kept: test.py:176-180) and emit compact records.
+__global__ void __launch_bounds__(NMS_THREADS, 1)
+cap_emit_kernel(const float4* __restrict__ pred, int r, int C, int max_per_image, int max_det, int* __restrict__ keep,
+                int* __restrict__ keep_cnt, const float* __restrict__ keep_score, float* __restrict__ det, int* __restrict__ ndet) {
+  __shared__ unsigned hist[256];
+  __shared__ unsigned s_prefix, s_kth;
+  __shared__ int s_total;
+  __shared__ int s_off[1025];
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    int t = 0;
+    for (int c = 1; c < C; ++c) t += keep_cnt[c];
+    s_total = t;
+  }
+  __syncthreads();
+  const int total = s_total;
+  unsigned thresh_bits = 0u;   // keep everything
+  if (max_per_image > 0 && total > max_per_image) {
+    unsigned prefix = 0u; int kth = max_per_image;   // kth largest, 1-based
+    for (int pass = 3; pass >= 0; --pass) {
+      if (tid < 256) hist[tid] = 0u;
+      __syncthreads();
+      const unsigned hi_mask = pass == 3 ? 0u : (0xffffffffu << ((pass + 1) * 8));
+      for (int i = tid; i < (C - 1) * r; i += blockDim.x) {
+        const int c = 1 + i / r, j = i % r;
+        if (j < keep_cnt[c]) {
+          const unsigned u = __float_as_uint(keep_score[(size_t)c * r + j]);
+          if ((u & hi_mask) == (prefix & hi_mask)) atomicAdd(&hist[(u >> (pass * 8)) & 255u], 1u);
+        }
+      }
+      __syncthreads();
+      if (tid == 0) {
+        int acc = 0; int b = 255;
+        for (; b >= 0; --b) { if (acc + (int)hist[b] >= kth) break; acc += (int)hist[b]; }
+        s_prefix = prefix | ((unsigned)b << (pass * 8));
+        s_kth = (unsigned)(kth - acc);
+      }
+      __syncthreads();
+      prefix = s_prefix; kth = (int)s_kth;
+      __syncthreads();
+    }
+    thresh_bits = prefix;
+  }
+  // filter each class list in place (order preserved), thread per class
+  if (tid < C && tid >= 1) {
+    const int cnt = keep_cnt[tid];
+    int o = 0;
+    for (int j = 0; j < cnt; ++j) {
+      const unsigned u = __float_as_uint(keep_score[(size_t)tid * r + j]);
+      if (u >= thresh_bits) { keep[(size_t)tid * r + o] = keep[(size_t)tid * r + j]; ++o; }
+    }
+    for (int j = o; j < cnt; ++j) keep[(size_t)tid * r + j] = -1;
+    keep_cnt[tid] = o;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int acc = 0;
+    s_off[0] = 0; s_off[1] = 0;
+    for (int c = 1; c < C; ++c) { s_off[c] = acc; acc += keep_cnt[c]; }
+    s_off[C] = acc;
+    *ndet = acc < max_det ? acc : max_det;
+  }
+  __syncthreads();
+  for (int i = tid; i < (C - 1) * r; i += blockDim.x) {
+    const int c = 1 + i / r, j = i % r;
+    if (j < keep_cnt[c]) {
+      const int slot = s_off[c] + j;
+      if (slot < max_det) {
+        const int roi = keep[(size_t)c * r + j];
+        const float4 b = __ldg(pred + (size_t)roi * C + c);
+        float* d = det + (size_t)slot * 6;
+        d[0] = b.x; d[1] = b.y; d[2] = b.z; d[3] = b.w;
+        d[4] = 0.f; d[5] = (float)c;
+      }
+    }
+  }
+}
+
+// scores for the records are re-read from probs to avoid depending on the (compacted) keep_score order
+__global__ void fill_det_scores_kernel(const float* __restrict__ probs, int C, const int* __restrict__ keep, const int* __restrict__ keep_cnt,
+                                       int r, int max_det, float* __restrict__ det) {
+  // thread per class walks its list; offsets recomputed by prefix over keep_cnt (C is tiny)
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < 1 || c >= C) return;
+  int off = 0;
+  for (int k = 1; k < c; ++k) off += keep_cnt[k];
+  for (int j = 0; j < keep_cnt[c]; ++j) {
+    const int slot = off + j;
+    if (slot >= max_det) break;
+    det[(size_t)slot * 6 + 4] = __ldg(probs + (size_t)keep[(size_t)c * r + j] * C + c);
+  }
+}
+
+__global__ void iota_kernel(int* p, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = i;
+}
+
+}  // namespace frcnn
+
+using namespace frcnn;
+
+extern "C" size_t frcnn_sort_workspace_bytes(int n) {
+  size_t temp = 0;
+  cub::DeviceRadixSort::SortPairsDescending(nullptr, temp, (const float*)nullptr, (float*)nullptr, (const int*)nullptr, (int*)nullptr, n);
+  return ((temp + 255) / 256) * 256 + (size_t)n * sizeof(int) + 256;
+}
+
+// NOTE: the key sort itself is CUB's radix sort (CUDA toolkit header library) -- the one library kernel on the
+// path; stable, so equal scores keep ascending index order (= the oracle's tie rule).
+extern "C" int frcnn_sort_desc(const float* keys, int n, int* order, float* sorted_keys, void* workspace, size_t workspace_bytes, void* stream) {
+  FRCNN_REQUIRE(keys && order && sorted_keys && workspace && n > 0, "sort_desc: bad argument");
+  FRCNN_REQUIRE(workspace_bytes >= frcnn_sort_workspace_bytes(n), "sort_desc: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  int* iota = reinterpret_cast<int*>(workspace);
+  const size_t iota_bytes = (((size_t)n * sizeof(int)) + 255) / 256 * 256;
+  void* temp = reinterpret_cast<uint8_t*>(workspace) + iota_bytes;
+  size_t temp_bytes = workspace_bytes - iota_bytes;
+  iota_kernel<<<cdiv(n, 256), 256, 0, st>>>(iota, n);
+  FRCNN_LAUNCH_CHECK();
+  FRCNN_CUDA(cub::DeviceRadixSort::SortPairsDescending(temp, temp_bytes, keys, sorted_keys, (const int*)iota, order, n, 0, 32, st));
+  return OK;
+}
+
+extern "C" int frcnn_proposals(const float* props, const float* scores, const int* order, int n, int pre_nms_top_n,
+                               int post_nms_top_n, float thresh, unsigned flags, float* rois, float* roi_scores, int* keep,
+                               int* num, void* stream) {
+  FRCNN_REQUIRE(props && scores && order && rois && roi_scores && keep && num && n > 0 && post_nms_top_n > 0, "proposals: bad argument");
+  const int m = (pre_nms_top_n > 0 && pre_nms_top_n < n) ? pre_nms_top_n : n;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (thresh < 0.f) {
+    gather_top_kernel<<<cdiv(post_nms_top_n, 256), 256, 0, st>>>(reinterpret_cast<const float4*>(props), scores, order, m,
+                                                                 post_nms_top_n, rois, roi_scores, keep, num);
+  } else {
+    if (post_nms_top_n > PROPOSAL_CAP) { set_error("proposals: post_nms_top_n %d > capacity %d", post_nms_top_n, PROPOSAL_CAP); return ERR_CAPACITY; }
+    proposals_kernel<<<1, NMS_THREADS, 0, st>>>(reinterpret_cast<const float4*>(props), scores, order, m, post_nms_top_n, thresh,
+                                                flags, rois, roi_scores, keep, num);
+  }
+  FRCNN_LAUNCH_CHECK();
+  return OK;
+}
+
+// workspace for the global kept set, grown on demand (per process, single stream use)
+static float4* g_kept = nullptr; static float* g_kept_area = nullptr; static int g_kept_cap = 0;
+static int ensure_kept(int n) {
+  if (n <= g_kept_cap) return OK;
+  if (g_kept) { cudaFree(g_kept); cudaFree(g_kept_area); g_kept = nullptr; g_kept_area = nullptr; g_kept_cap = 0; }
+  FRCNN_CUDA(cudaMalloc(&g_kept, (size_t)n * sizeof(float4)));
+  FRCNN_CUDA(cudaMalloc(&g_kept_area, (size_t)n * sizeof(float)));
+  g_kept_cap = n;
+  return OK;
+}
+
+extern "C" int frcnn_nms_sorted_dev(const float* boxes, int n, float thresh, unsigned flags, int max_out, int* keep, int* num, void* stream) {
+  FRCNN_REQUIRE(boxes && keep && num && n > 0 && max_out > 0, "nms_sorted_dev: bad argument");
+  int rc = ensure_kept(max_out < n ? max_out : n);
+  if (rc) return rc;
+  nms_sorted_kernel<<<1, NMS_THREADS, 0, (cudaStream_t)stream>>>(boxes, 4, n, thresh, flags, max_out, g_kept, g_kept_area, keep, num);
+  FRCNN_LAUNCH_CHECK();
+  return OK;
+}
+
+extern "C" int frcnn_nms_host(int* keep_out, int* num_out, const float* boxes_host, int boxes_num, int boxes_dim, float thresh,
+                              int device_id, unsigned flags) {
+  FRCNN_REQUIRE(keep_out && num_out, "nms_host: null output");
+  *num_out = 0;
+  if (boxes_num <= 0) return OK;
+  FRCNN_REQUIRE(boxes_host && boxes_dim >= 4, "nms_host: bad input");
+  int cur = -1;
+  FRCNN_CUDA(cudaGetDevice(&cur));
+  if (cur != device_id) FRCNN_CUDA(cudaSetDevice(device_id));
+  float* dboxes = nullptr; int* dkeep = nullptr; int* dnum = nullptr;
+  int rc = ensure_kept(boxes_num);
+  if (rc) return rc;
+  cudaError_t e = cudaMalloc(&dboxes, (size_t)boxes_num * boxes_dim * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&dkeep, (size_t)(boxes_num + 1) * sizeof(int));
+  if (e == cudaSuccess) {
+    dnum = dkeep + boxes_num;
+    e = cudaMemcpy(dboxes, boxes_host, (size_t)boxes_num * boxes_dim * sizeof(float), cudaMemcpyHostToDevice);
+  }
+  if (e == cudaSuccess) {
+    nms_sorted_kernel<<<1, NMS_THREADS>>>(dboxes, boxes_dim, boxes_num, thresh, flags, boxes_num, g_kept, g_kept_area, dkeep, dnum);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(num_out, dnum, sizeof(int), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && *num_out > 0) e = cudaMemcpy(keep_out, dkeep, (size_t)(*num_out) * sizeof(int), cudaMemcpyDeviceToHost);
+  cudaFree(dboxes); cudaFree(dkeep);
+  if (e != cudaSuccess) return cuda_fail(e, "frcnn_nms_host", __FILE__, __LINE__);
+  return OK;
+}
+
+extern "C" int frcnn_detect_post(const float* cls_prob, const float* pred_boxes, const int* num_rois, int r, int num_classes,
+                                 float score_thresh, float nms_thresh, unsigned flags, int max_per_image, int max_det,
+                                 float* det, int* ndet, int* keep, int* keep_cnt, float* keep_score, void* stream) {
+  FRCNN_REQUIRE(cls_prob && pred_boxes && num_rois && det && ndet && keep && keep_cnt && keep_score, "detect_post: null pointer");
+  FRCNN_REQUIRE(r > 0 && r <= DET_CAP && num_classes >= 2 && num_classes <= 1024, "detect_post: r<=%d, 2<=C<=1024 required", DET_CAP);
+  cudaStream_t st = (cudaStream_t)stream;
+  class_nms_kernel<<<num_classes - 1, NMS_THREADS, 0, st>>>(cls_prob, reinterpret_cast<const float4*>(pred_boxes), num_rois, r,
+                                                           num_classes, score_thresh, nms_thresh, flags, keep, keep_cnt, keep_score);
+  FRCNN_LAUNCH_CHECK();
+  cap_emit_kernel<<<1, NMS_THREADS, 0, st>>>(reinterpret_cast<const float4*>(pred_boxes), r, num_classes, max_per_image, max_det,
+                                            keep, keep_cnt, keep_score, det, ndet);
+  FRCNN_LAUNCH_CHECK();
+  fill_det_scores_kernel<<<cdiv(num_classes, 128), 128, 0, st>>>(cls_prob, num_classes, keep, keep_cnt, r, max_det, det);
+  FRCNN_LAUNCH_CHECK();
+  return OK;
+}

@@ -1,0 +1,406 @@
+// Bandwidth-bound stages of the TEST graph as coalesced / float4-vectorised SIMT kernels (fp32).
+// Where the oracle (numpy, no FMA) performs separate roundings the kernels use __f*_rn intrinsics so that
+// nvcc cannot contract them; reference file:line citations are in include/frcnn_b200.h.
+#include "common.cuh"
+#include "../../include/frcnn_b200.h"
+
+namespace frcnn {
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == FRCNN_ACT_RELU) return fmaxf(v, 0.f);
+  if (act == FRCNN_ACT_RELU6) return fminf(fmaxf(v, 0.f), 6.f);
+  return v;
+}
+
+// ---- weight packing: HWIO -> [cout][kh*kw*cin] hi/lo tf32 planes ---------------------------------------
+__global__ void pack_weights_kernel(const float* __restrict__ w, float* __restrict__ hi, float* __restrict__ lo,
+                                    int ktot, int cout) {
+  const size_t total = (size_t)ktot * cout;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int k = (int)(i % ktot);
+    const int co = (int)(i / ktot);
+    const float v = w[(size_t)k * cout + co];
+    const float h = to_tf32(v);
+    hi[i] = h;
+    lo[i] = to_tf32(__fsub_rn(v, h));
+  }
+}
+
+// ---- first-layer convolution, cin == 3 ------------------------------------------------------------------
+// thread = (output pixel, group of 8 output channels); filter bank staged in shared memory.
+template <int CG>
+__global__ void conv_first_kernel(const float* __restrict__ in, const float* __restrict__ w,
+                                  const float* __restrict__ scale, const float* __restrict__ shift,
+                                  float* __restrict__ out, int n, int h, int wd, int cout, int k, int stride,
+                                  int pad_t, int pad_l, int ho, int wo, int act) {
+  extern __shared__ float wsm[];  // [k*k*3][cout]
+  const int wcount = k * k * 3 * cout;
+  for (int i = threadIdx.x; i < wcount; i += blockDim.x) wsm[i] = w[i];
+  __syncthreads();
+  const int groups = cout / CG;
+  const long total = (long)n * ho * wo * groups;
+  const long gid = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= total) return;
+  const int g = (int)(gid % groups);
+  const long pix = gid / groups;
+  const int ox = (int)(pix % wo);
+  const int oy = (int)((pix / wo) % ho);
+  const int b = (int)(pix / ((long)wo * ho));
+  float acc[CG];
+#pragma unroll
+  for (int i = 0; i < CG; ++i) acc[i] = 0.f;
+  const int iy0 = oy * stride - pad_t, ix0 = ox * stride - pad_l;
+  for (int r = 0; r < k; ++r) {
+    const int iy = iy0 + r;
+    if (iy < 0 || iy >= h) continue;
+    for (int s = 0; s < k; ++s) {
+      const int ix = ix0 + s;
+      if (ix < 0 || ix >= wd) continue;
+      const float* ip = in + (((size_t)b * h + iy) * wd + ix) * 3;
+      const float x0 = __ldg(ip), x1 = __ldg(ip + 1), x2 = __ldg(ip + 2);
+      const float* wp = wsm + ((r * k + s) * 3) * cout + g * CG;
+#pragma unroll
+      for (int i = 0; i < CG; ++i) {
+        acc[i] = fmaf(x0, wp[i], acc[i]);
+        acc[i] = fmaf(x1, wp[cout + i], acc[i]);
+        acc[i] = fmaf(x2, wp[2 * cout + i], acc[i]);
+      }
+    }
+  }
+  float* op = out + (size_t)pix * cout + g * CG;
+#pragma unroll
+  for (int i = 0; i < CG; ++i) {
+    float v = acc[i];
+    const int c = g * CG + i;
+    if (scale) v = __fmul_rn(v, __ldg(scale + c));
+    if (shift) v = __fadd_rn(v, __ldg(shift + c));
+    acc[i] = apply_act(v, act);
+  }
+#pragma unroll
+  for (int i = 0; i < CG; i += 4) *reinterpret_cast<float4*>(op + i) = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
+}
+
+// ---- depthwise 3x3 ---------------------------------------------------------------------------------------
+__global__ void depthwise3x3_kernel(const float* __restrict__ in, const float* __restrict__ w,
+                                    const float* __restrict__ scale, const float* __restrict__ shift,
+                                    float* __restrict__ out, int n, int h, int wd, int c, int stride, int pad_t,
+                                    int pad_l, int ho, int wo, int act) {
+  const int c4 = c >> 2;
+  const long total = (long)n * ho * wo * c4;
+  const long gid = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= total) return;
+  const int cg = (int)(gid % c4);
+  const long pix = gid / c4;
+  const int ox = (int)(pix % wo);
+  const int oy = (int)((pix / wo) % ho);
+  const int b = (int)(pix / ((long)wo * ho));
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const int iy = oy * stride - pad_t + r;
+    if (iy < 0 || iy >= h) continue;
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+      const int ix = ox * stride - pad_l + s;
+      if (ix < 0 || ix >= wd) continue;
+      const float4 x = __ldg(reinterpret_cast<const float4*>(in + (((size_t)b * h + iy) * wd + ix) * c) + cg);
+      const float4 k4 = __ldg(reinterpret_cast<const float4*>(w + (size_t)(r * 3 + s) * c) + cg);
+      acc.x = fmaf(x.x, k4.x, acc.x); acc.y = fmaf(x.y, k4.y, acc.y);
+      acc.z = fmaf(x.z, k4.z, acc.z); acc.w = fmaf(x.w, k4.w, acc.w);
+    }
+  }
+  float v[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int ch = cg * 4 + i;
+    if (scale) v[i] = __fmul_rn(v[i], __ldg(scale + ch));
+    if (shift) v[i] = __fadd_rn(v[i], __ldg(shift + ch));
+    v[i] = apply_act(v[i], act);
+  }
+  reinterpret_cast<float4*>(out + (size_t)pix * c)[cg] = make_float4(v[0], v[1], v[2], v[3]);
+}
+
+// ---- max pool ----------------------------------------------------------------------------------------------
+__global__ void max_pool_kernel(const float* __restrict__ in, float* __restrict__ out, int n, int h, int wd, int c,
+                                int k, int stride, int pad_t, int pad_l, int ho, int wo, int pad_neg_inf) {
+  const int c4 = c >> 2;
+  const long total = (long)n * ho * wo * c4;
+  const long gid = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= total) return;
+  const int cg = (int)(gid % c4);
+  const long pix = gid / c4;
+  const int ox = (int)(pix % wo);
+  const int oy = (int)((pix / wo) % ho);
+  const int b = (int)(pix / ((long)wo * ho));
+  const float ninf = __int_as_float(0xff800000);
+  float4 m = make_float4(ninf, ninf, ninf, ninf);
+  for (int r = 0; r < k; ++r) {
+    const int iy = oy * stride - pad_t + r;
+    for (int s = 0; s < k; ++s) {
+      const int ix = ox * stride - pad_l + s;
+      float4 x;
+      if (iy < 0 || iy >= h || ix < 0 || ix >= wd) {
+        if (pad_neg_inf) continue;
+        x = make_float4(0.f, 0.f, 0.f, 0.f);
+      } else {
+        x = __ldg(reinterpret_cast<const float4*>(in + (((size_t)b * h + iy) * wd + ix) * c) + cg);
+      }
+      m.x = fmaxf(m.x, x.x); m.y = fmaxf(m.y, x.y); m.z = fmaxf(m.z, x.z); m.w = fmaxf(m.w, x.w);
+    }
+  }
+  reinterpret_cast<float4*>(out + (size_t)pix * c)[cg] = m;
+}
+
+// ---- spatial mean -------------------------------------------------------------------------------------------
+__global__ void spatial_mean_kernel(const float* __restrict__ in, float* __restrict__ out, int r, int hw, int c) {
+  const int c4 = c >> 2;
+  const long gid = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (long)r * c4) return;
+  const int cg = (int)(gid % c4);
+  const int row = (int)(gid / c4);
+  const float4* p = reinterpret_cast<const float4*>(in + (size_t)row * hw * c) + cg;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = 0; i < hw; ++i) {
+    const float4 x = __ldg(p + (size_t)i * c4);
+    s.x = __fadd_rn(s.x, x.x); s.y = __fadd_rn(s.y, x.y); s.z = __fadd_rn(s.z, x.z); s.w = __fadd_rn(s.w, x.w);
+  }
+  const float d = (float)hw;
+  reinterpret_cast<float4*>(out + (size_t)row * c)[cg] =
+      make_float4(__fdiv_rn(s.x, d), __fdiv_rn(s.y, d), __fdiv_rn(s.z, d), __fdiv_rn(s.w, d));
+}
+
+// ---- crop_and_resize (+ 2x2 max) ---------------------------------------------------------------------------
+__device__ __forceinline__ float lerp_rn(float a, float b, float t) { return __fadd_rn(a, __fmul_rn(__fsub_rn(b, a), t)); }
+
+__device__ __forceinline__ float4 bilinear4(const float* __restrict__ feat, int fh, int fw, int c, int cg, float in_y,
+                                            float in_x) {
+  if (in_y < 0.f || in_y > (float)(fh - 1) || in_x < 0.f || in_x > (float)(fw - 1)) return make_float4(0.f, 0.f, 0.f, 0.f);
+  const float ty = floorf(in_y), lx = floorf(in_x);
+  const int top = (int)ty, bot = (int)ceilf(in_y), lef = (int)lx, rig = (int)ceilf(in_x);
+  const float yl = __fsub_rn(in_y, ty), xl = __fsub_rn(in_x, lx);
+  const float4 tl = __ldg(reinterpret_cast<const float4*>(feat + ((size_t)top * fw + lef) * c) + cg);
+  const float4 tr = __ldg(reinterpret_cast<const float4*>(feat + ((size_t)top * fw + rig) * c) + cg);
+  const float4 bl = __ldg(reinterpret_cast<const float4*>(feat + ((size_t)bot * fw + lef) * c) + cg);
+  const float4 br = __ldg(reinterpret_cast<const float4*>(feat + ((size_t)bot * fw + rig) * c) + cg);
+  float4 o;
+  o.x = lerp_rn(lerp_rn(tl.x, tr.x, xl), lerp_rn(bl.x, br.x, xl), yl);
+  o.y = lerp_rn(lerp_rn(tl.y, tr.y, xl), lerp_rn(bl.y, br.y, xl), yl);
+  o.z = lerp_rn(lerp_rn(tl.z, tr.z, xl), lerp_rn(bl.z, br.z, xl), yl);
+  o.w = lerp_rn(lerp_rn(tl.w, tr.w, xl), lerp_rn(bl.w, br.w, xl), yl);
+  return o;
+}
+
+__global__ void crop_pool_kernel(const float* __restrict__ feat, int fh, int fw, int c, const float* __restrict__ rois,
+                                 int r, int pooled, int pre_pool, float* __restrict__ out) {
+  const int c4 = c >> 2;
+  const long total = (long)r * pooled * pooled * c4;
+  const long gid = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= total) return;
+  const int cg = (int)(gid % c4);
+  long t = gid / c4;
+  const int px = (int)(t % pooled); t /= pooled;
+  const int py = (int)(t % pooled);
+  const int ri = (int)(t / pooled);
+  const float* roi = rois + (size_t)ri * 5;
+  // network.py:146-153: normalise by (dim-1)*16, then crop_and_resize's own un-normalisation
+  const float hh = __fmul_rn(__fsub_rn((float)fh, 1.f), 16.f);
+  const float ww = __fmul_rn(__fsub_rn((float)fw, 1.f), 16.f);
+  const float x1 = __fdiv_rn(__ldg(roi + 1), ww), y1 = __fdiv_rn(__ldg(roi + 2), hh);
+  const float x2 = __fdiv_rn(__ldg(roi + 3), ww), y2 = __fdiv_rn(__ldg(roi + 4), hh);
+  const int crop = pre_pool ? 2 * pooled : pooled;
+  const float hs = __fdiv_rn(__fmul_rn(__fsub_rn(y2, y1), (float)(fh - 1)), (float)(crop - 1));
+  const float ws = __fdiv_rn(__fmul_rn(__fsub_rn(x2, x1), (float)(fw - 1)), (float)(crop - 1));
+  const float by = __fmul_rn(y1, (float)(fh - 1)), bx = __fmul_rn(x1, (float)(fw - 1));
+  float4 o;
+  if (!pre_pool) {
+    o = bilinear4(feat, fh, fw, c, cg, __fadd_rn(by, __fmul_rn((float)py, hs)), __fadd_rn(bx, __fmul_rn((float)px, ws)));
+  } else {
+    const float ninf = __int_as_float(0xff800000);
+    o = make_float4(ninf, ninf, ninf, ninf);
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const float4 v = bilinear4(feat, fh, fw, c, cg, __fadd_rn(by, __fmul_rn((float)(2 * py + dy), hs)),
+                                   __fadd_rn(bx, __fmul_rn((float)(2 * px + dx), ws)));
+        o.x = fmaxf(o.x, v.x); o.y = fmaxf(o.y, v.y); o.z = fmaxf(o.z, v.z); o.w = fmaxf(o.w, v.w);
+      }
+  }
+  reinterpret_cast<float4*>(out + (size_t)(((size_t)ri * pooled + py) * pooled + px) * c)[cg] = o;
+}
+
+// ---- RPN decode ---------------------------------------------------------------------------------------------
+__global__ void rpn_decode_kernel(const float* __restrict__ rpn, int ld, int delta_col, const float* __restrict__ base, int A, int fh,
+                                  int fw, int feat_stride, float im_h, float im_w, float* __restrict__ scores,
+                                  float* __restrict__ props) {
+  const int total = fh * fw * A;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int a = i % A, pos = i / A;
+  const int gx = pos % fw, gy = pos / fw;
+  const float* row = rpn + (size_t)pos * ld;
+  const float bg = __ldg(row + a), fg = __ldg(row + A + a);
+  const float m = fmaxf(bg, fg);
+  const float e0 = expf(__fsub_rn(bg, m)), e1 = expf(__fsub_rn(fg, m));
+  scores[i] = __fdiv_rn(e1, __fadd_rn(e0, e1));
+  const float sx = (float)(gx * feat_stride), sy = (float)(gy * feat_stride);
+  const float ax1 = __ldg(base + a * 4 + 0) + sx, ay1 = __ldg(base + a * 4 + 1) + sy;
+  const float ax2 = __ldg(base + a * 4 + 2) + sx, ay2 = __ldg(base + a * 4 + 3) + sy;
+  const float4 d = *reinterpret_cast<const float4*>(row + delta_col + 4 * a);
+  const float w = __fadd_rn(__fsub_rn(ax2, ax1), 1.f), h = __fadd_rn(__fsub_rn(ay2, ay1), 1.f);
+  const float cx = __fadd_rn(ax1, __fmul_rn(0.5f, w)), cy = __fadd_rn(ay1, __fmul_rn(0.5f, h));
+  const float pcx = __fadd_rn(__fmul_rn(d.x, w), cx), pcy = __fadd_rn(__fmul_rn(d.y, h), cy);
+  const float pw = __fmul_rn(expf(d.z), w), ph = __fmul_rn(expf(d.w), h);
+  const float xmax = __fsub_rn(im_w, 1.f), ymax = __fsub_rn(im_h, 1.f);
+  float4 o;
+  o.x = fmaxf(fminf(__fsub_rn(pcx, __fmul_rn(0.5f, pw)), xmax), 0.f);
+  o.y = fmaxf(fminf(__fsub_rn(pcy, __fmul_rn(0.5f, ph)), ymax), 0.f);
+  o.z = fmaxf(fminf(__fadd_rn(pcx, __fmul_rn(0.5f, pw)), xmax), 0.f);
+  o.w = fmaxf(fminf(__fadd_rn(pcy, __fmul_rn(0.5f, ph)), ymax), 0.f);
+  reinterpret_cast<float4*>(props)[i] = o;
+}
+
+// ---- classification tail --------------------------------------------------------------------------------------
+// one warp per RoI row: softmax over C logits + de-normalised deltas
+__global__ void cls_finish_kernel(const float* __restrict__ head, int ld, int r, int C, float4 stds, float4 means,
+                                  float* __restrict__ cls_score, float* __restrict__ cls_prob, float* __restrict__ bbox) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= r) return;
+  const float* hr = head + (size_t)row * ld;
+  float m = __int_as_float(0xff800000);
+  for (int c = lane; c < C; c += 32) m = fmaxf(m, __ldg(hr + c));
+  for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) s += expf(__fsub_rn(__ldg(hr + c), m));
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  for (int c = lane; c < C; c += 32) {
+    const float x = __ldg(hr + c);
+    cls_score[(size_t)row * C + c] = x;
+    cls_prob[(size_t)row * C + c] = __fdiv_rn(expf(__fsub_rn(x, m)), s);
+  }
+  const float sd[4] = {stds.x, stds.y, stds.z, stds.w};
+  const float mn[4] = {means.x, means.y, means.z, means.w};
+  for (int j = lane; j < 4 * C; j += 32)
+    bbox[(size_t)row * 4 * C + j] = __fadd_rn(__fmul_rn(__ldg(hr + C + j), sd[j & 3]), mn[j & 3]);
+}
+
+// im_detect tail: thread per (roi, class)
+__global__ void bbox_decode_kernel(const float* __restrict__ rois, const float* __restrict__ deltas, int r, int C,
+                                   float im_scale, float xmax, float ymax, float* __restrict__ pred) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= r * C) return;
+  const int row = i / C;
+  const float* roi = rois + (size_t)row * 5;
+  const float x1 = __fdiv_rn(__ldg(roi + 1), im_scale), y1 = __fdiv_rn(__ldg(roi + 2), im_scale);
+  const float x2 = __fdiv_rn(__ldg(roi + 3), im_scale), y2 = __fdiv_rn(__ldg(roi + 4), im_scale);
+  const float w = __fadd_rn(__fsub_rn(x2, x1), 1.f), h = __fadd_rn(__fsub_rn(y2, y1), 1.f);
+  const float cx = __fadd_rn(x1, __fmul_rn(0.5f, w)), cy = __fadd_rn(y1, __fmul_rn(0.5f, h));
+  const float4 d = reinterpret_cast<const float4*>(deltas)[i];
+  const float pcx = __fadd_rn(__fmul_rn(d.x, w), cx), pcy = __fadd_rn(__fmul_rn(d.y, h), cy);
+  const float pw = __fmul_rn(expf(d.z), w), ph = __fmul_rn(expf(d.w), h);
+  float4 o;
+  o.x = fmaxf(__fsub_rn(pcx, __fmul_rn(0.5f, pw)), 0.f);
+  o.y = fmaxf(__fsub_rn(pcy, __fmul_rn(0.5f, ph)), 0.f);
+  o.z = fminf(__fadd_rn(pcx, __fmul_rn(0.5f, pw)), xmax);
+  o.w = fminf(__fadd_rn(pcy, __fmul_rn(0.5f, ph)), ymax);
+  reinterpret_cast<float4*>(pred)[i] = o;
+}
+
+static inline unsigned blocks_for(long total, int threads) { return (unsigned)((total + threads - 1) / threads); }
+
+}  // namespace frcnn
+
+using namespace frcnn;
+
+extern "C" int frcnn_pack_conv_weights(const float* w, float* hi, float* lo, int kh, int kw, int cin, int cout, void* stream) {
+  FRCNN_REQUIRE(w && hi && lo && kh > 0 && kw > 0 && cin > 0 && cout > 0, "bad argument");
+  const int ktot = kh * kw * cin;
+  const long total = (long)ktot * cout;
+  unsigned blocks = blocks_for(total, 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  pack_weights_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, hi, lo, ktot, cout);
+  FRCNN_LAUNCH_CHECK();
+  return OK;
+}
+
+extern "C" int frcnn_conv_first(const float* in, const float* w, const float* scale, const float* shift, float* out, int n,
+                                int h, int wd, int cout, int k, int stride, int pad_t, int pad_l, int ho, int wo, int act,
+                                void* stream) {
+  FRCNN_REQUIRE(in && w && out && cout % 8 == 0, "conv_first: cout must be a multiple of 8");
+  const size_t smem = (size_t)k * k * 3 * cout * sizeof(float);
+  FRCNN_REQUIRE(smem <= 48 * 1024, "conv_first: filter bank %zu B exceeds 48 KiB", smem);
+  const long total = (long)n * ho * wo * (cout / 8);
+  conv_first_kernel<8><<<blocks_for(total, 256), 256, smem, (cudaStream_t)stream>>>(in, w, scale, shift, out, n, h, wd, cout, k,
+                                                                                  stride, pad_t, pad_l, ho, wo, act);
+  FRCNN_LAUNCH_CHECK();
+  return OK;
+}
+
+extern "C" int frcnn_depthwise3x3(const float* in, const float* w, const float* scale, const float* shift, float* out, int n,
+                                  int h, int wd, int c, int stride, int pad_t, int pad_l, int ho, int wo, int act, void* stream) {
+  FRCNN_REQUIRE(in && w && out && c % 4 == 0, "depthwise: c must be a multiple of 4");
+  const long total = (long)n * ho * wo * (c / 4);
+  depthwise3x3_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(in, w, scale, shift, out, n, h, wd, c, stride,
+                                                                              pad_t, pad_l, ho, wo, act);
+  FRCNN_LAUNCH_CHECK();
+  return OK;
+}
+
+extern "C" int frcnn_max_pool(const float* in, float* out, int n, int h, int wd, int c, int k, int stride, int pad_t, int pad_l,
+                              int ho, int wo, int pad_is_neg_inf, void* stream) {
+  FRCNN_REQUIRE(in && out && c % 4 == 0, "max_pool: c must be a multiple of 4");
+  const long total = (long)n * ho * wo * (c / 4);
+  max_pool_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(in, out, n, h, wd, c, k, stride, pad_t, pad_l, ho, wo,
+                                                                          pad_is_neg_inf);
+  FRCNN_LAUNCH_CHECK();
+  return OK;
+}
+
+extern "C" int frcnn_spatial_mean(const float* in, float* out, int r, int hw, int c, void* stream) {
+  FRCNN_REQUIRE(in && out && c % 4 == 0, "spatial_mean: c must be a multiple of 4");
+  spatial_mean_kernel<<<blocks_for((long)r * (c / 4), 256), 256, 0, (cudaStream_t)stream>>>(in, out, r, hw, c);
+  FRCNN_LAUNCH_CHECK();
+  return OK;
+}
+
+extern "C" int frcnn_crop_pool(const float* feat, int fh, int fw, int c, const float* rois, int r, int pooled, int pre_pool,
+                               float* out, void* stream) {
+  FRCNN_REQUIRE(feat && rois && out && c % 4 == 0 && pooled > 1, "crop_pool: bad argument");
+  const long total = (long)r * pooled * pooled * (c / 4);
+  crop_pool_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(feat, fh, fw, c, rois, r, pooled, pre_pool, out);
+  FRCNN_LAUNCH_CHECK();
+  return OK;
+}
+
+extern "C" int frcnn_rpn_decode(const float* rpn_out, int ld, int delta_col, const float* base_anchors, int num_anchors, int fh, int fw,
+                                int feat_stride, float im_h, float im_w, float* scores, float* props, void* stream) {
+  FRCNN_REQUIRE(rpn_out && base_anchors && scores && props, "rpn_decode: null pointer");
+  FRCNN_REQUIRE(delta_col >= 2 * num_anchors && ld >= delta_col + 4 * num_anchors && (ld % 4) == 0 && (delta_col % 4) == 0,
+                "rpn_decode: ld/delta_col alignment");
+  const int total = fh * fw * num_anchors;
+  rpn_decode_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(rpn_out, ld, delta_col, base_anchors, num_anchors, fh, fw,
+                                                                            feat_stride, im_h, im_w, scores, props);
+  FRCNN_LAUNCH_CHECK();
+  return OK;
+}
+
+extern "C" int frcnn_cls_finish(const float* head_out, int ld, int r, int num_classes, const float* stds4, const float* means4,
+                                float* cls_score, float* cls_prob, float* bbox_pred, void* stream) {
+  FRCNN_REQUIRE(head_out && stds4 && means4 && cls_score && cls_prob && bbox_pred, "cls_finish: null pointer");
+  const float4 sd = make_float4(stds4[0], stds4[1], stds4[2], stds4[3]);
+  const float4 mn = make_float4(means4[0], means4[1], means4[2], means4[3]);
+  cls_finish_kernel<<<blocks_for((long)r * 32, 256), 256, 0, (cudaStream_t)stream>>>(head_out, ld, r, num_classes, sd, mn, cls_score,
+                                                                                   cls_prob, bbox_pred);
+  FRCNN_LAUNCH_CHECK();
+  return OK;
+}
+
+extern "C" int frcnn_bbox_decode(const float* rois, const float* bbox_pred, int r, int num_classes, float im_scale, int orig_h,
+                                 int orig_w, float* pred_boxes, void* stream) {
+  FRCNN_REQUIRE(rois && bbox_pred && pred_boxes, "bbox_decode: null pointer");
+  bbox_decode_kernel<<<blocks_for((long)r * num_classes, 256), 256, 0, (cudaStream_t)stream>>>(
+      rois, bbox_pred, r, num_classes, im_scale, (float)(orig_w - 1), (float)(orig_h - 1), pred_boxes);
+  FRCNN_LAUNCH_CHECK();
+  return OK;
+}

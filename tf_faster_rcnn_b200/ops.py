@@ -1,0 +1,182 @@
+"""Stage-level Python entry points over the C ABI.  torch is used ONLY for device memory
+(`torch.empty(..., device='cuda')`, `.data_ptr()`) and the current CUDA stream; every op below
+launches hand-written sm_100a kernels from libfrcnn_b200.so.  No CPU fallbacks.
+"""
+import ctypes as C
+import numpy as np
+import torch
+
+from . import _native as N
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _f32(t):
+    assert t.dtype == torch.float32 and t.is_cuda and t.is_contiguous(), "expected contiguous cuda fp32"
+    return t
+
+
+def same_pads(n, k, s):
+    """TF 'SAME' padding (before, after) for one dimension."""
+    out = -(-n // s)
+    total = max((out - 1) * s + k - n, 0)
+    return total // 2, total - total // 2
+
+
+class PackedConv:
+    """Device-resident K-major hi/lo weight planes + epilogue vectors of one conv / FC layer."""
+
+    def __init__(self, w_hwio, scale=None, shift=None):
+        w = torch.as_tensor(np.ascontiguousarray(w_hwio), dtype=torch.float32).cuda()
+        if w.dim() == 2:                     # FC [in,out] == 1x1 conv
+            w = w.view(1, 1, w.shape[0], w.shape[1])
+        self.kh, self.kw, self.cin, self.cout = (int(v) for v in w.shape)
+        ktot = self.kh * self.kw * self.cin
+        self.w_hi = torch.empty((self.cout, ktot), dtype=torch.float32, device="cuda")
+        self.w_lo = torch.empty_like(self.w_hi)
+        N.check(N.lib().frcnn_pack_conv_weights(_p(w), _p(self.w_hi), _p(self.w_lo), self.kh, self.kw, self.cin,
+                                                self.cout, _stream()), "pack_conv_weights")
+        torch.cuda.current_stream().synchronize()
+        self.scale = None if scale is None else torch.as_tensor(np.ascontiguousarray(scale), dtype=torch.float32).cuda()
+        self.shift = None if shift is None else torch.as_tensor(np.ascontiguousarray(shift), dtype=torch.float32).cuda()
+
+
+class ConvPlan:
+    """frcnn_conv_plan bound to fixed input/output/residual buffers (TMA descriptors hold raw pointers)."""
+
+    def __init__(self, x, pc, out, stride=1, pad_t=0, pad_l=0, act=N.ACT_NONE, residual=None, block_n=0):
+        _f32(x); _f32(out)
+        n, h, w, cin = x.shape
+        assert cin == pc.cin, (cin, pc.cin)
+        no, ho, wo, co = out.shape
+        assert no == n and co == pc.cout
+        d = N.ConvDesc(_p(x), _p(pc.w_hi), _p(pc.w_lo), _p(pc.scale), _p(pc.shift), _p(residual), _p(out),
+                       n, h, w, cin, pc.cout, pc.kh, pc.kw, stride, pad_t, pad_l, ho, wo, act, block_n)
+        self._h = C.c_void_p()
+        N.check(N.lib().frcnn_conv_plan_create(C.byref(self._h), C.byref(d)), "conv_plan_create")
+        self._keep = (x, pc, out, residual)
+
+    def run(self):
+        N.check(N.lib().frcnn_conv_plan_run(self._h, _stream()), "conv_plan_run")
+
+    def info(self):
+        v = [C.c_int() for _ in range(8)]
+        N.check(N.lib().frcnn_conv_plan_info(self._h, *[C.byref(a) for a in v]), "conv_plan_info")
+        return dict(zip(["block_n", "tile_n", "tile_h", "tile_w", "grid_m", "grid_n", "stages", "smem"], [a.value for a in v]))
+
+    def __del__(self):
+        try:
+            if self._h:
+                N.lib().frcnn_conv_plan_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+
+def conv_out_hw(h, w, k, stride, mode):
+    """mode 'SAME' (TF) or 'EXPLICIT' (slim conv2d_same: pad (k-1)//2 before, rest after, then VALID)."""
+    if mode == "SAME":
+        pt, _ = same_pads(h, k, stride)
+        pl, _ = same_pads(w, k, stride)
+        return -(-h // stride), -(-w // stride), pt, pl
+    pb = (k - 1) // 2
+    return (h + k - 1 - k) // stride + 1, (w + k - 1 - k) // stride + 1, pb, pb
+
+
+def conv_first(x, w_hwio_dev, scale, shift, out, k, stride, pad_t, pad_l, act):
+    n, h, w, _ = x.shape
+    _, ho, wo, co = out.shape
+    N.check(N.lib().frcnn_conv_first(_p(_f32(x)), _p(w_hwio_dev), _p(scale), _p(shift), _p(_f32(out)), n, h, w, co, k, stride,
+                                     pad_t, pad_l, ho, wo, act, _stream()), "conv_first")
+
+
+def depthwise3x3(x, w_dev, scale, shift, out, stride, pad_t, pad_l, act):
+    n, h, w, c = x.shape
+    _, ho, wo, _ = out.shape
+    N.check(N.lib().frcnn_depthwise3x3(_p(_f32(x)), _p(w_dev), _p(scale), _p(shift), _p(_f32(out)), n, h, w, c, stride, pad_t,
+                                       pad_l, ho, wo, act, _stream()), "depthwise3x3")
+
+
+def max_pool(x, out, k, stride, pad_t, pad_l, pad_is_neg_inf):
+    n, h, w, c = x.shape
+    _, ho, wo, _ = out.shape
+    N.check(N.lib().frcnn_max_pool(_p(_f32(x)), _p(_f32(out)), n, h, w, c, k, stride, pad_t, pad_l, ho, wo,
+                                   int(pad_is_neg_inf), _stream()), "max_pool")
+
+
+def spatial_mean(x, out):
+    r, hw, c = x.shape[0], x.shape[1] * x.shape[2], x.shape[3]
+    N.check(N.lib().frcnn_spatial_mean(_p(_f32(x)), _p(_f32(out)), r, hw, c, _stream()), "spatial_mean")
+
+
+def rpn_decode(rpn_out, delta_col, base_anchors, num_anchors, fh, fw, im_h, im_w, scores, props, feat_stride=16):
+    ld = rpn_out.shape[-1]
+    N.check(N.lib().frcnn_rpn_decode(_p(_f32(rpn_out)), ld, delta_col, _p(base_anchors), num_anchors, fh, fw, feat_stride,
+                                     float(im_h), float(im_w), _p(scores), _p(props), _stream()), "rpn_decode")
+
+
+def sort_workspace(n):
+    return torch.empty(int(N.lib().frcnn_sort_workspace_bytes(n)), dtype=torch.uint8, device="cuda")
+
+
+def sort_desc(keys, order, sorted_keys, workspace):
+    n = keys.numel()
+    N.check(N.lib().frcnn_sort_desc(_p(_f32(keys)), n, _p(order), _p(sorted_keys), _p(workspace), workspace.numel(), _stream()),
+            "sort_desc")
+
+
+def proposals(props, scores, order, pre_nms_top_n, post_nms_top_n, thresh, flags, rois, roi_scores, keep, num):
+    n = scores.numel()
+    N.check(N.lib().frcnn_proposals(_p(props), _p(scores), _p(order), n, pre_nms_top_n, post_nms_top_n, float(thresh), flags,
+                                    _p(rois), _p(roi_scores), _p(keep), _p(num), _stream()), "proposals")
+
+
+def crop_pool(feat, rois, pooled, pre_pool, out):
+    _, fh, fw, c = feat.shape
+    r = rois.shape[0]
+    N.check(N.lib().frcnn_crop_pool(_p(_f32(feat)), fh, fw, c, _p(_f32(rois)), r, pooled, int(pre_pool), _p(_f32(out)), _stream()),
+            "crop_pool")
+
+
+def cls_finish(head_out, num_classes, stds, means, cls_score, cls_prob, bbox_pred):
+    r, ld = head_out.shape
+    s4 = (C.c_float * 4)(*[float(v) for v in stds])
+    m4 = (C.c_float * 4)(*[float(v) for v in means])
+    N.check(N.lib().frcnn_cls_finish(_p(_f32(head_out)), ld, r, num_classes, s4, m4, _p(cls_score), _p(cls_prob), _p(bbox_pred),
+                                     _stream()), "cls_finish")
+
+
+def bbox_decode(rois, bbox_pred, num_classes, im_scale, orig_h, orig_w, pred_boxes):
+    r = rois.shape[0]
+    N.check(N.lib().frcnn_bbox_decode(_p(_f32(rois)), _p(_f32(bbox_pred)), r, num_classes, float(np.float32(im_scale)), int(orig_h),
+                                      int(orig_w), _p(pred_boxes), _stream()), "bbox_decode")
+
+
+def detect_post(cls_prob, pred_boxes, num_rois, num_classes, score_thresh, nms_thresh, flags, max_per_image, det, ndet, keep,
+                keep_cnt, keep_score):
+    r = cls_prob.shape[0]
+    N.check(N.lib().frcnn_detect_post(_p(cls_prob), _p(pred_boxes), _p(num_rois), r, num_classes, float(score_thresh),
+                                      float(nms_thresh), flags, max_per_image, det.shape[0], _p(det), _p(ndet), _p(keep),
+                                      _p(keep_cnt), _p(keep_score), _stream()), "detect_post")
+
+
+def nms_sorted_dev(boxes, thresh, flags, max_out, keep, num):
+    N.check(N.lib().frcnn_nms_sorted_dev(_p(_f32(boxes)), boxes.shape[0], float(thresh), flags, max_out, _p(keep), _p(num),
+                                         _stream()), "nms_sorted_dev")
+
+
+def nms_host(sorted_dets, thresh, flags, device_id=0):
+    """`_nms`-compatible call on HOST arrays (already sorted by descending score)."""
+    d = np.ascontiguousarray(sorted_dets, dtype=np.float32)
+    n = d.shape[0]
+    keep = np.empty(max(n, 1), dtype=np.int32)
+    num = C.c_int(0)
+    N.check(N.lib().frcnn_nms_host(keep.ctypes.data_as(N.ip), C.byref(num), d.ctypes.data_as(N.fp), n, d.shape[1] if n else 5,
+                                   float(thresh), device_id, flags), "nms_host")
+    return keep[:num.value].copy()
