@@ -91,6 +91,7 @@ typedef struct {
   int ho, wo;
   int act;                   /* FRCNN_ACT_* */
   int block_n;               /* 0 = choose; else 32/64/128 */
+  int kb_per_chunk;          /* 0 = default (2): 32-wide k-blocks summed in TMEM before promotion to registers */
 } frcnn_conv_desc;
 
 int frcnn_conv_plan_create(frcnn_conv_plan** out, const frcnn_conv_desc* d);

@@ -10,6 +10,13 @@ import numpy as np
 F = np.float32
 
 
+def exp_f32(x):
+    """fp32 exp, correctly rounded (computed in fp64, rounded once).  The reference calls np.exp /
+    tf.exp on fp32 (bbox_transform.py:52-53,103-104), each a <=1-ulp libm-grade exp that differs between
+    numpy/Eigen builds; the oracle pins the one well-defined member of that family."""
+    return np.exp(np.asarray(x, dtype=np.float64)).astype(F)
+
+
 def decode(boxes, deltas):
     """bbox_transform_inv: boxes fp32 [R,4], deltas fp32 [R,4K] -> fp32 [R,4K]."""
     boxes = np.ascontiguousarray(boxes, dtype=F)
@@ -22,8 +29,8 @@ def decode(boxes, deltas):
     cy = boxes[:, 1:2] + F(0.5) * h
     pcx = deltas[:, 0::4] * w + cx
     pcy = deltas[:, 1::4] * h + cy
-    pw = np.exp(deltas[:, 2::4]) * w
-    ph = np.exp(deltas[:, 3::4]) * h
+    pw = exp_f32(deltas[:, 2::4]) * w
+    ph = exp_f32(deltas[:, 3::4]) * h
     out = np.empty_like(deltas)
     out[:, 0::4] = pcx - F(0.5) * pw
     out[:, 1::4] = pcy - F(0.5) * ph

@@ -23,7 +23,7 @@ def ref64(x, w, stride, pad_t, pad_l, ho, wo):
     return y.permute(0, 2, 3, 1).numpy()[:, :ho, :wo]
 
 
-def run_conv(x, w, stride, mode, scale=None, shift=None, residual=None, act=0, block_n=0):
+def run_conv(x, w, stride, mode, scale=None, shift=None, residual=None, act=0, block_n=0, kb_per_chunk=0, time_it=False):
     from tf_faster_rcnn_b200 import ops
     n, h, wd, cin = x.shape
     k = w.shape[0]
@@ -32,10 +32,22 @@ def run_conv(x, w, stride, mode, scale=None, shift=None, residual=None, act=0, b
     xd = torch.from_numpy(x).cuda()
     out = torch.full((n, ho, wo, w.shape[3]), float("nan"), dtype=torch.float32, device="cuda")
     rd = None if residual is None else torch.from_numpy(residual).cuda()
-    plan = ops.ConvPlan(xd, pc, out, stride, pt, pl, act, rd, block_n)
+    plan = ops.ConvPlan(xd, pc, out, stride, pt, pl, act, rd, block_n, kb_per_chunk)
     plan.run()
     torch.cuda.synchronize()
-    return out.cpu().numpy(), plan.info(), (ho, wo, pt, pl)
+    info = plan.info()
+    if time_it:
+        for _ in range(3):
+            plan.run()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):
+            plan.run()
+        e1.record()
+        torch.cuda.synchronize()
+        info["us"] = e0.elapsed_time(e1) * 1000 / 20
+        info["tflops"] = 2.0 * n * ho * wo * w.shape[3] * k * k * cin / (info["us"] * 1e-6) / 1e12
+    return out.cpu().numpy(), info, (ho, wo, pt, pl)
 
 
 CASES = [
@@ -92,3 +104,28 @@ def test_conv_epilogue_bn_residual_relu(cuda):
     assert err < 2e-5
     got6, _, _ = run_conv(x, wt, 1, "SAME", scale=None, shift=beta, act=2)
     assert np.abs(got6 - L.relu6(conv + beta)).max() < 2e-5
+
+
+@pytest.mark.parametrize("shape", [("k3136_fc", 1, 1, 300, 3136, 128, 1), ("vgg_conv5", 1, 38, 50, 512, 512, 3),
+                                   ("vgg_conv3", 1, 150, 200, 256, 256, 3), ("res_head_pw", 300, 7, 7, 2048, 512, 1),
+                                   ("res_head_c3", 300, 7, 7, 512, 512, 3), ("res_b3_pw", 1, 38, 50, 1024, 256, 1)])
+def test_accumulation_chunk_sweep(cuda, shape):
+    """Accuracy and speed as a function of kb_per_chunk (k-blocks summed in TMEM before promotion)."""
+    name, n, h, w, cin, cout, k = shape
+    rng = np.random.default_rng(1)
+    x = np.maximum(rng.standard_normal((n, h, w, cin)), 0).astype(F)      # post-ReLU-like
+    wt = (rng.standard_normal((k, k, cin, cout)) * np.sqrt(2.0 / (k * k * cin))).astype(F)
+    want64 = None
+    for kpc in (1, 2, 4, 8, 100000):
+        for bn in ((0,) if kpc != 2 else (0, 32, 64, 128)):
+            got, info, (ho, wo, pt, pl) = run_conv(x, wt, 1, "SAME", block_n=bn, kb_per_chunk=kpc, time_it=True)
+            if want64 is None:
+                want64 = ref64(x, wt, 1, pt, pl, ho, wo)
+                want32 = L.conv2d(x, wt, 1, "SAME")
+                print("\n[%s] oracle fp32 vs f64: %.2e" % (name, np.abs(want32 - want64).max() / np.abs(want64).max()))
+            e = np.abs(got - want64).max() / np.abs(want64).max()
+            print("[%s] kb_per_chunk=%d bn=%d grid=%dx%d tile=%dx%dx%d  err=%.2e  %.1f us  %.1f TFLOP/s" %
+                  (name, kpc, info["block_n"], info["grid_m"], info["grid_n"], info["tile_n"], info["tile_h"], info["tile_w"],
+                   e, info["us"], info["tflops"]))
+            if kpc <= 2:
+                assert e < 4e-6

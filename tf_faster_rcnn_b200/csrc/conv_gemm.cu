@@ -12,12 +12,19 @@
 // convolution's zero padding -- no im2col buffer ever exists.  The box lands as <=128 rows x 128 B with
 // SWIZZLE_128B, exactly the K-major UMMA operand layout.  Weights are pre-split (hi/lo planes) and K-major.
 //
-// Warp roles (192 threads, 1 CTA/SM):
+// Accumulation: the tensor core adds into its fp32 accumulator with truncation (measured: error grows
+// linearly with the number of MMA steps, ~2.4e-5 relative at K=3136), so accumulation is two-level: TMEM holds
+// only the partial sum of a short chunk of k-blocks (double buffered), which the epilogue warps add into fp32
+// REGISTER accumulators with round-to-nearest adds while the MMA warp works on the other TMEM buffer.
+//
+// Warp roles (320 threads, 1 CTA/SM):
 //   warp 0      TMA producer            full[s]  <- tx bytes
 //   warps 2..5  operand splitter        wait full[s]; A -> (A_hi in place, A_lo) in smem; fence.proxy.async;
 //                                       arrive ready[s]           (elementwise => swizzle-agnostic)
-//   warp 1      MMA issuer (1 thread)   wait ready[s]; 4 k-slices x 3 tcgen05.mma; tcgen05.commit -> empty[s]
-//   warps 2..5  epilogue                wait tmem_full; tcgen05.ld; y = act(acc*scale + shift (+res)); st.global
+//   warp 1      MMA issuer (1 thread)   wait ready[s]; 4 k-slices x 3 tcgen05.mma; tcgen05.commit -> empty[s];
+//                                       per chunk: wait tmem_empty[b] ... commit -> tmem_full[b]
+//   warps 6..9  accumulate + epilogue   per chunk: wait tmem_full[b]; tcgen05.ld; acc += partial; arrive
+//                                       tmem_empty[b]; finally y = act(acc*scale + shift (+res)); st.global
 #include "common.cuh"
 #include "../../include/frcnn_b200.h"
 #include <stdlib.h>
@@ -28,8 +35,9 @@ namespace frcnn {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 32;                          // fp32 elements: 128 B = one swizzle row
 constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 4;  // 16 KiB
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 320;
 constexpr int SPLIT_THREADS = 128;
+constexpr int EPI_THREADS = 128;
 
 struct ConvKernelParams {
   float* out;
@@ -42,6 +50,7 @@ struct ConvKernelParams {
   int kh, kw, cin, stride, pad_t, pad_l;
   int act;
   int a_box_bytes;
+  int kb_per_chunk;   // k-blocks accumulated in TMEM before promotion to registers
 };
 
 template <int BN> struct StageCfg;
@@ -77,8 +86,9 @@ conv_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
   uint64_t* ready = full + kStages;
   uint64_t* empty = ready + kStages;
-  uint64_t* tmem_full = empty + kStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  uint64_t* tmem_full = empty + kStages;      // [2]
+  uint64_t* tmem_empty = tmem_full + 2;       // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -91,14 +101,15 @@ conv_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   const int w0 = tile_w * p.tw, h0 = tile_h * p.th, n0 = tile_n * p.tn;
   const int nblk = blockIdx.y;
   const int num_kb = p.kh * p.kw * (p.cin / BLOCK_K);
+  const int num_chunks = (num_kb + p.kb_per_chunk - 1) / p.kb_per_chunk;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmBhi); tma_prefetch_desc(&tmBlo);
     for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&ready[s], SPLIT_THREADS); mbar_init(&empty[s], 1); }
-    mbar_init(tmem_full, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], EPI_THREADS); }
     mbar_fence_init();
   }
-  if (warp == 1) { tmem_alloc(tmem_slot, BN); tmem_relinquish(); }
+  if (warp == 1) { tmem_alloc(tmem_slot, 2 * BN); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -125,89 +136,108 @@ conv_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   } else if (warp == 1) {
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(&ready[stage], phase);
+      int kb = 0;
+      for (int c = 0; c < num_chunks; ++c) {
+        const int b = c & 1;
+        mbar_wait(&tmem_empty[b], ((uint32_t)(c >> 1) & 1u) ^ 1u);   // buffer drained by the epilogue warps
         tc_fence_after();
-        const uint32_t sbase = smem_u32(smem + stage * kStageBytes);
-        const uint64_t a_hi = sw128_desc(sbase);
-        const uint64_t a_lo = sw128_desc(sbase + A_TILE_BYTES);
-        const uint64_t b_hi = sw128_desc(sbase + 2 * A_TILE_BYTES);
-        const uint64_t b_lo = sw128_desc(sbase + 2 * A_TILE_BYTES + kBTile);
+        const uint32_t tmem_d = tmem_base + (uint32_t)(b * BN);
+        const int kb_end = min(num_kb, kb + p.kb_per_chunk);
+        bool first = true;
+        for (; kb < kb_end; ++kb) {
+          mbar_wait(&ready[stage], phase);
+          tc_fence_after();
+          const uint32_t sbase = smem_u32(smem + stage * kStageBytes);
+          const uint64_t a_hi = sw128_desc(sbase);
+          const uint64_t a_lo = sw128_desc(sbase + A_TILE_BYTES);
+          const uint64_t b_hi = sw128_desc(sbase + 2 * A_TILE_BYTES);
+          const uint64_t b_lo = sw128_desc(sbase + 2 * A_TILE_BYTES + kBTile);
 #pragma unroll
-        for (int k = 0; k < BLOCK_K / 8; ++k) {
-          const uint64_t off = (uint64_t)(k * 8 * 4) >> 4;   // advance 8 tf32 = 32 B inside the swizzle row
-          umma_tf32(tmem_base, a_lo + off, b_hi + off, kIdesc, (kb > 0 || k > 0) ? 1u : 0u);
-          umma_tf32(tmem_base, a_hi + off, b_lo + off, kIdesc, 1u);
-          umma_tf32(tmem_base, a_hi + off, b_hi + off, kIdesc, 1u);
+          for (int k = 0; k < BLOCK_K / 8; ++k) {
+            const uint64_t off = (uint64_t)(k * 8 * 4) >> 4;   // advance 8 tf32 = 32 B inside the swizzle row
+            umma_tf32(tmem_d, a_lo + off, b_hi + off, kIdesc, first ? 0u : 1u);
+            first = false;
+            umma_tf32(tmem_d, a_hi + off, b_lo + off, kIdesc, 1u);
+            umma_tf32(tmem_d, a_hi + off, b_hi + off, kIdesc, 1u);
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&empty[stage]);
-        if (++stage == kStages) { stage = 0; phase ^= 1; }
+        umma_commit(&tmem_full[b]);
       }
-      umma_commit(tmem_full);
     }
     __syncwarp();
-  } else {
+  } else if (warp < 6) {
     // ---------------- operand splitter ----------------
     const int t = threadIdx.x - 64;
-    {
-      int stage = 0; uint32_t phase = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(&full[stage], phase);
-        float4* a = reinterpret_cast<float4*>(smem + stage * kStageBytes);
-        float4* alo = reinterpret_cast<float4*>(smem + stage * kStageBytes + A_TILE_BYTES);
+    int stage = 0; uint32_t phase = 0;
+    for (int kb = 0; kb < num_kb; ++kb) {
+      mbar_wait(&full[stage], phase);
+      float4* a = reinterpret_cast<float4*>(smem + stage * kStageBytes);
+      float4* alo = reinterpret_cast<float4*>(smem + stage * kStageBytes + A_TILE_BYTES);
 #pragma unroll
-        for (int i = 0; i < A_TILE_BYTES / 16 / SPLIT_THREADS; ++i) {
-          const int idx = i * SPLIT_THREADS + t;
-          float4 v = a[idx], h, l;
-          h.x = to_tf32(v.x); h.y = to_tf32(v.y); h.z = to_tf32(v.z); h.w = to_tf32(v.w);
-          l.x = to_tf32(__fsub_rn(v.x, h.x)); l.y = to_tf32(__fsub_rn(v.y, h.y));
-          l.z = to_tf32(__fsub_rn(v.z, h.z)); l.w = to_tf32(__fsub_rn(v.w, h.w));
-          a[idx] = h; alo[idx] = l;
-        }
-        fence_proxy_async_smem();
-        mbar_arrive(&ready[stage]);
-        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      for (int i = 0; i < A_TILE_BYTES / 16 / SPLIT_THREADS; ++i) {
+        const int idx = i * SPLIT_THREADS + t;
+        float4 v = a[idx], h, l;
+        h.x = to_tf32(v.x); h.y = to_tf32(v.y); h.z = to_tf32(v.z); h.w = to_tf32(v.w);
+        l.x = to_tf32(__fsub_rn(v.x, h.x)); l.y = to_tf32(__fsub_rn(v.y, h.y));
+        l.z = to_tf32(__fsub_rn(v.z, h.z)); l.w = to_tf32(__fsub_rn(v.w, h.w));
+        a[idx] = h; alo[idx] = l;
       }
+      fence_proxy_async_smem();
+      mbar_arrive(&ready[stage]);
+      if (++stage == kStages) { stage = 0; phase ^= 1; }
+    }
+  } else {
+    // ---------------- accumulate (TMEM chunk partials -> fp32 registers, RN adds) ----------------
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    float acc[BN];
+#pragma unroll
+    for (int j = 0; j < BN; ++j) acc[j] = 0.f;
+    for (int c = 0; c < num_chunks; ++c) {
+      const int b = c & 1;
+      mbar_wait(&tmem_full[b], (uint32_t)(c >> 1) & 1u);
+      tc_fence_after();
+#pragma unroll
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * BN + c0), v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[c0 + j] = __fadd_rn(acc[c0 + j], __uint_as_float(v[j]));
+      }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty[b]);
     }
     // ---------------- epilogue ----------------
-    mbar_wait(tmem_full, 0);
-    tc_fence_after();
-    const int q = warp & 3;                 // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;
     const int rows_img = p.th * p.tw;
     const int dn = row / rows_img, rem = row % rows_img;
     const int dh = rem / p.tw, dw = rem % p.tw;
     const int n = n0 + dn, h = h0 + dh, w = w0 + dw;
     const bool valid = (row < p.tn * rows_img) && n < p.nimg && h < p.ho && w < p.wo;
-    const size_t pix = valid ? (((size_t)n * p.ho + h) * p.wo + w) : 0;
-    float* orow = p.out + pix * p.cout;
-    const float* rrow = p.residual ? p.residual + pix * p.cout : nullptr;
-    const bool vec_ok = (p.cout & 3) == 0;
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      const int cbase = nblk * BN + c0;
-      if (cbase >= p.cout) break;
-      uint32_t v[32];
-      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-      tmem_ld_wait();
-      if (valid) {
+    if (valid) {
+      const size_t pix = ((size_t)n * p.ho + h) * p.wo + w;
+      float* orow = p.out + pix * p.cout;
+      const float* rrow = p.residual ? p.residual + pix * p.cout : nullptr;
+      const bool vec_ok = (p.cout & 3) == 0;
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const int c = cbase + j;
-          if (c >= p.cout) break;
+      for (int j = 0; j < BN; j += 4) {
+        const int c = nblk * BN + j;
+        if (c < p.cout) {
           float y[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            float acc = __uint_as_float(v[j + e]);
+            float a = acc[j + e];
             const int ce = c + e;
             if (ce < p.cout) {
-              if (p.scale) acc = __fmul_rn(acc, __ldg(p.scale + ce));
-              if (p.shift) acc = __fadd_rn(acc, __ldg(p.shift + ce));
-              if (rrow) acc = __fadd_rn(acc, __ldg(rrow + ce));
-              if (p.act == FRCNN_ACT_RELU) acc = fmaxf(acc, 0.f);
-              else if (p.act == FRCNN_ACT_RELU6) acc = fminf(fmaxf(acc, 0.f), 6.f);
+              if (p.scale) a = __fmul_rn(a, __ldg(p.scale + ce));
+              if (p.shift) a = __fadd_rn(a, __ldg(p.shift + ce));
+              if (rrow) a = __fadd_rn(a, __ldg(rrow + ce));
+              if (p.act == FRCNN_ACT_RELU) a = fmaxf(a, 0.f);
+              else if (p.act == FRCNN_ACT_RELU6) a = fminf(fmaxf(a, 0.f), 6.f);
             }
-            y[e] = acc;
+            y[e] = a;
           }
           if (vec_ok) {
             *reinterpret_cast<float4*>(orow + c) = make_float4(y[0], y[1], y[2], y[3]);
@@ -218,10 +248,10 @@ conv_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         }
       }
     }
-    tc_fence_before();
   }
+  tc_fence_before();
   __syncthreads();
-  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, BN); }
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 2 * BN); }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -369,6 +399,7 @@ extern "C" int frcnn_conv_plan_create(frcnn_conv_plan** out, const frcnn_conv_de
   k.kh = d->kh; k.kw = d->kw; k.cin = d->cin; k.stride = d->stride; k.pad_t = d->pad_t; k.pad_l = d->pad_l;
   k.act = d->act;
   k.a_box_bytes = tn * th * tw * BLOCK_K * 4;
+  k.kb_per_chunk = d->kb_per_chunk > 0 ? d->kb_per_chunk : 2;
   p->block_n = bn;
   p->stages = bn == 128 ? StageCfg<128>::kStages : bn == 64 ? StageCfg<64>::kStages : StageCfg<32>::kStages;
   p->smem = bn == 128 ? smem_bytes<128>() : bn == 64 ? smem_bytes<64>() : smem_bytes<32>();

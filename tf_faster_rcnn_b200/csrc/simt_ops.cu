@@ -170,6 +170,9 @@ __global__ void spatial_mean_kernel(const float* __restrict__ in, float* __restr
 }
 
 // ---- crop_and_resize (+ 2x2 max) ---------------------------------------------------------------------------
+// correctly-rounded fp32 exp (via fp64) for the two box-size terms: the oracle defines exp the same way
+__device__ __forceinline__ float exp_cr(float x) { return (float)exp((double)x); }
+
 __device__ __forceinline__ float lerp_rn(float a, float b, float t) { return __fadd_rn(a, __fmul_rn(__fsub_rn(b, a), t)); }
 
 __device__ __forceinline__ float4 bilinear4(const float* __restrict__ feat, int fh, int fw, int c, int cg, float in_y,
@@ -250,7 +253,7 @@ __global__ void rpn_decode_kernel(const float* __restrict__ rpn, int ld, int del
   const float w = __fadd_rn(__fsub_rn(ax2, ax1), 1.f), h = __fadd_rn(__fsub_rn(ay2, ay1), 1.f);
   const float cx = __fadd_rn(ax1, __fmul_rn(0.5f, w)), cy = __fadd_rn(ay1, __fmul_rn(0.5f, h));
   const float pcx = __fadd_rn(__fmul_rn(d.x, w), cx), pcy = __fadd_rn(__fmul_rn(d.y, h), cy);
-  const float pw = __fmul_rn(expf(d.z), w), ph = __fmul_rn(expf(d.w), h);
+  const float pw = __fmul_rn(exp_cr(d.z), w), ph = __fmul_rn(exp_cr(d.w), h);
   const float xmax = __fsub_rn(im_w, 1.f), ymax = __fsub_rn(im_h, 1.f);
   float4 o;
   o.x = fmaxf(fminf(__fsub_rn(pcx, __fmul_rn(0.5f, pw)), xmax), 0.f);
@@ -298,7 +301,7 @@ __global__ void bbox_decode_kernel(const float* __restrict__ rois, const float* 
   const float cx = __fadd_rn(x1, __fmul_rn(0.5f, w)), cy = __fadd_rn(y1, __fmul_rn(0.5f, h));
   const float4 d = reinterpret_cast<const float4*>(deltas)[i];
   const float pcx = __fadd_rn(__fmul_rn(d.x, w), cx), pcy = __fadd_rn(__fmul_rn(d.y, h), cy);
-  const float pw = __fmul_rn(expf(d.z), w), ph = __fmul_rn(expf(d.w), h);
+  const float pw = __fmul_rn(exp_cr(d.z), w), ph = __fmul_rn(exp_cr(d.w), h);
   float4 o;
   o.x = fmaxf(__fsub_rn(pcx, __fmul_rn(0.5f, pw)), 0.f);
   o.y = fmaxf(__fsub_rn(pcy, __fmul_rn(0.5f, ph)), 0.f);
