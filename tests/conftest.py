@@ -6,6 +6,8 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+from tf_faster_rcnn_b200 import paths as _paths  # noqa: E402
+_paths.add_lib_path()
 
 
 def pytest_configure(config):

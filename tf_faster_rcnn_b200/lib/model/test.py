@@ -1,0 +1,136 @@
+"""Inference driver with the reference's entry points (lib/model/test.py): _get_image_blob :26-58,
+im_detect :86-107, apply_nms :109-136, test_net :138-192.
+
+im_detect keeps the reference data flow (host blob -> net.test_image -> decode -> clip) but the decode/clip
+run in a device kernel right behind the CUDA graph (frcnn_bbox_decode) instead of NumPy.  test_net by default
+also keeps the per-class NMS + max_per_image cap on the device (frcnn_detect_post); setting
+`FUSED_POST = False` runs the reference's Python loop over `nms()` instead (same results)."""
+import os
+import pickle
+
+import cv2
+import numpy as np
+import torch
+
+from model.config import cfg, get_output_dir
+from model.nms_wrapper import nms
+from utils.blob import im_list_to_blob
+from utils.timer import Timer
+
+FUSED_POST = True
+
+
+def _get_image_blob(im):
+    """BGR uint8 image -> ([1,H,W,3] fp32 blob, scale factors): mean-subtract, resize so the short side is
+    TEST.SCALES[i] unless that would push the long side over TEST.MAX_SIZE."""
+    pixels = im.astype(np.float32, copy=True)
+    pixels -= cfg.PIXEL_MEANS
+    short_side, long_side = min(pixels.shape[:2]), max(pixels.shape[:2])
+    resized, factors = [], []
+    for target in cfg.TEST.SCALES:
+        f = float(target) / float(short_side)
+        if np.round(f * long_side) > cfg.TEST.MAX_SIZE:
+            f = float(cfg.TEST.MAX_SIZE) / float(long_side)
+        resized.append(cv2.resize(pixels, None, None, fx=f, fy=f, interpolation=cv2.INTER_LINEAR))
+        factors.append(f)
+    return im_list_to_blob(resized), np.array(factors)
+
+
+def _get_blobs(im):
+    data, factors = _get_image_blob(im)
+    return {'data': data}, factors
+
+
+def im_detect(sess, net, im):
+    """-> scores [R, C] fp32, pred_boxes [R, 4C] fp32 in ORIGINAL-image pixels."""
+    blobs, im_scales = _get_blobs(im)
+    assert len(im_scales) == 1, "Only single-image batch implemented"
+    blob = blobs['data']
+    blobs['im_info'] = np.array([blob.shape[1], blob.shape[2], im_scales[0]], dtype=np.float32)
+    plan = net._run(blob, blobs['im_info'], post=True, detect=False, orig_hw=im.shape[:2])
+    torch.cuda.current_stream().synchronize()
+    r = int(plan.num_rois.item())
+    scores = plan.cls_prob[:r].cpu().numpy()
+    if cfg.TEST.BBOX_REG:
+        pred_boxes = plan.pred_boxes[:r].cpu().numpy()
+    else:
+        boxes = plan.rois[:r, 1:5].cpu().numpy() / np.float32(im_scales[0])
+        pred_boxes = np.tile(boxes, (1, scores.shape[1]))
+    return scores, pred_boxes
+
+
+def apply_nms(all_boxes, thresh):
+    """NMS over already-collected detections all_boxes[cls][image] (used by tools/reval.py)."""
+    out = [[[] for _ in range(len(all_boxes[0]))] for _ in range(len(all_boxes))]
+    for c, per_image in enumerate(all_boxes):
+        for i, dets in enumerate(per_image):
+            if len(dets) == 0:
+                continue
+            ok = np.where((dets[:, 2] > dets[:, 0]) & (dets[:, 3] > dets[:, 1]))[0]
+            dets = dets[ok, :]
+            if len(dets) == 0:
+                continue
+            keep = nms(dets, thresh)
+            if len(keep):
+                out[c][i] = dets[keep, :].copy()
+    return out
+
+
+def _detections_python_loop(scores, boxes, num_classes, thresh, max_per_image):
+    """test.py:162-180 verbatim flow over the (GPU) nms()."""
+    per_class = [np.zeros((0, 5), np.float32)]
+    for j in range(1, num_classes):
+        inds = np.where(scores[:, j] > thresh)[0]
+        cls_dets = np.hstack((boxes[inds, j * 4:(j + 1) * 4], scores[inds, j][:, np.newaxis])).astype(np.float32, copy=False)
+        keep = nms(cls_dets, cfg.TEST.NMS)
+        per_class.append(cls_dets[keep, :])
+    if max_per_image > 0:
+        image_scores = np.hstack([d[:, -1] for d in per_class[1:]])
+        if len(image_scores) > max_per_image:
+            image_thresh = np.sort(image_scores)[-max_per_image]
+            per_class = [per_class[0]] + [d[d[:, -1] >= image_thresh, :] for d in per_class[1:]]
+    return per_class
+
+
+def detect_image(net, im, thresh=0., max_per_image=100):
+    """One image through the fused device path -> list over classes of fp32 [k,5] (x1,y1,x2,y2,score)."""
+    blobs, im_scales = _get_blobs(im)
+    blob = blobs['data']
+    im_info = np.array([blob.shape[1], blob.shape[2], im_scales[0]], dtype=np.float32)
+    net.options["score_thresh"], net.options["max_per_image"] = float(thresh), int(max_per_image)
+    net.options["nms_thresh"] = cfg.TEST.NMS
+    det, _ = net.detect(blob, im_info, im.shape[:2])
+    C = net.num_classes
+    cls = det[:, 5].astype(np.int64)
+    return [det[cls == j, :5] for j in range(C)]
+
+
+def test_net(sess, net, imdb, weights_filename, max_per_image=100, thresh=0.):
+    """Run the detector over imdb; all_boxes[cls][image] = [k,5]; pickles detections.pkl and evaluates."""
+    np.random.seed(cfg.RNG_SEED)
+    num_images = len(imdb.image_index)
+    all_boxes = [[[] for _ in range(num_images)] for _ in range(imdb.num_classes)]
+    output_dir = get_output_dir(imdb, weights_filename)
+    _t = {'im_detect': Timer(), 'misc': Timer()}
+    for i in range(num_images):
+        im = cv2.imread(imdb.image_path_at(i))
+        if FUSED_POST and cfg.TEST.BBOX_REG:
+            _t['im_detect'].tic()
+            per_class = detect_image(net, im, thresh, max_per_image)
+            _t['im_detect'].toc()
+            _t['misc'].tic()
+        else:
+            _t['im_detect'].tic()
+            scores, boxes = im_detect(sess, net, im)
+            _t['im_detect'].toc()
+            _t['misc'].tic()
+            per_class = _detections_python_loop(scores, boxes, imdb.num_classes, thresh, max_per_image)
+        for j in range(1, imdb.num_classes):
+            all_boxes[j][i] = per_class[j]
+        _t['misc'].toc()
+        print('im_detect: {:d}/{:d} {:.3f}s {:.3f}s'.format(i + 1, num_images, _t['im_detect'].average_time, _t['misc'].average_time))
+    with open(os.path.join(output_dir, 'detections.pkl'), 'wb') as f:
+        pickle.dump(all_boxes, f, pickle.HIGHEST_PROTOCOL)
+    print('Evaluating detections')
+    imdb.evaluate_detections(all_boxes, output_dir)
+    return all_boxes

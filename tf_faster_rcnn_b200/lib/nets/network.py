@@ -1,0 +1,123 @@
+"""`Network` base class with the reference's call surface (lib/nets/network.py):
+create_architecture :386-454, test_image :470-479, extract_head :464-467; subclasses implement
+_image_to_head / _head_to_tail (:380-384).  Instead of building a TF graph, create_architecture records
+the options; the first test_image for a blob shape builds a ShapePlan (device buffers, TMA-backed conv
+plans, CUDA graph) and later calls replay it.  `sess` arguments are accepted and ignored.
+"""
+import numpy as np
+import torch
+
+from model.config import cfg
+from layer_utils.generate_anchors import generate_anchors
+from tf_faster_rcnn_b200 import engine, _native
+
+_REGISTRY = []   # networks created in this process (the tensorflow shim's Saver.restore walks it)
+
+
+class Network(object):
+    def __init__(self):
+        self._feat_stride = [16, ]
+        self._predictions = {}
+        self._layers = {}
+        self._scope = None
+        self.weights = None
+        self._plans = {}
+        self.use_cuda_graph = True
+        _REGISTRY.append(self)
+
+    # ---- reference surface ---------------------------------------------------------------------------
+    def create_architecture(self, mode, num_classes, tag=None, anchor_scales=(8, 16, 32), anchor_ratios=(0.5, 1, 2)):
+        assert tag is not None
+        if mode != "TEST":
+            raise NotImplementedError("only the TEST-mode (inference) graph exists in this build")
+        self._mode, self._tag = mode, tag
+        self._num_classes = num_classes
+        self._anchor_scales, self._anchor_ratios = tuple(anchor_scales), tuple(anchor_ratios)
+        self._num_scales, self._num_ratios = len(anchor_scales), len(anchor_ratios)
+        self._num_anchors = self._num_scales * self._num_ratios
+        self.base_anchors = generate_anchors(ratios=np.array(self._anchor_ratios), scales=np.array(self._anchor_scales)).astype(np.float32)
+        self.anchor_key = "%s|%s" % (self._anchor_scales, self._anchor_ratios)
+        if cfg.POOLING_MODE != "crop":
+            raise NotImplementedError
+        self.options = dict(
+            test_mode=cfg.TEST.MODE, use_e2e_tf=bool(cfg.USE_E2E_TF), use_gpu_nms=bool(cfg.USE_GPU_NMS),
+            rpn_nms_thresh=cfg.TEST.RPN_NMS_THRESH, rpn_pre_nms_top_n=cfg.TEST.RPN_PRE_NMS_TOP_N,
+            rpn_post_nms_top_n=cfg.TEST.RPN_POST_NMS_TOP_N, rpn_top_n=cfg.TEST.RPN_TOP_N,
+            pooling_size=cfg.POOLING_SIZE, resnet_max_pool=bool(cfg.RESNET.MAX_POOL),
+            bbox_stds=tuple(cfg.TRAIN.BBOX_NORMALIZE_STDS), bbox_means=tuple(cfg.TRAIN.BBOX_NORMALIZE_MEANS),
+            nms_thresh=cfg.TEST.NMS, max_per_image=100, score_thresh=0.0, rpn_channels=cfg.RPN_CHANNELS,
+        )
+        if self.options["test_mode"] not in ("nms", "top"):
+            raise NotImplementedError
+        self._plans = {}
+        return {"rois": None}
+
+    def test_image(self, sess, image, im_info):
+        """-> (cls_score, cls_prob, bbox_pred, rois) host fp32 arrays, rois in blob-scale pixels."""
+        plan = self._run(image, im_info)
+        torch.cuda.current_stream().synchronize()
+        r = int(plan.num_rois.item())
+        out = (plan.cls_score[:r].cpu().numpy(), plan.cls_prob[:r].cpu().numpy(), plan.bbox_pred[:r].cpu().numpy(),
+               plan.rois[:r].cpu().numpy())
+        return out
+
+    def extract_head(self, sess, image):
+        plan = self._run(image, np.array([image.shape[1], image.shape[2], 1.0], np.float32))
+        torch.cuda.current_stream().synchronize()
+        return plan.feat.cpu().numpy()
+
+    def _image_to_head(self, tape, image):
+        raise NotImplementedError
+
+    def _head_to_tail(self, tape, pool5):
+        raise NotImplementedError
+
+    # ---- device side -------------------------------------------------------------------------------------
+    @property
+    def num_anchors(self):
+        return self._num_anchors
+
+    @property
+    def num_classes(self):
+        return self._num_classes
+
+    @property
+    def scope(self):
+        return self._scope
+
+    def crop_pre_pool(self):
+        """14x14 crop + 2x2 max pool (network.py:154-157) unless a subclass crops 7x7 directly."""
+        return True
+
+    def load_weights(self, tensors):
+        """tensors: dict TF-variable-name -> numpy array (HWIO convs, [in,out] FCs, BatchNorm stats)."""
+        self.weights = engine.Weights(dict(tensors))
+        self._plans = {}
+
+    def plan_for(self, h, w):
+        if self.weights is None:
+            raise RuntimeError("no weights loaded: call load_weights() / Saver.restore() before test_image")
+        key = (int(h), int(w))
+        if key not in self._plans:
+            _native.check(_native.lib().frcnn_check_device(torch.cuda.current_device()), "check_device")
+            self._plans[key] = engine.ShapePlan(self, key[0], key[1], use_graph=self.use_cuda_graph)
+        return self._plans[key]
+
+    def _run(self, image, im_info, post=False, detect=False, orig_hw=None):
+        assert image.shape[0] == 1 and image.shape[3] == 3, "Only single-image batch implemented"
+        plan = self.plan_for(image.shape[1], image.shape[2])
+        if isinstance(image, torch.Tensor):
+            plan.image.copy_(image, non_blocking=True)
+        else:
+            plan.image.copy_(torch.from_numpy(np.ascontiguousarray(image, dtype=np.float32)), non_blocking=True)
+        oh, ow = orig_hw if orig_hw is not None else (None, None)
+        plan.launch(float(im_info[2]), oh, ow, post=post, detect=detect)
+        return plan
+
+    def detect(self, image, im_info, orig_hw):
+        """Fused device path for im_detect + test_net's per-class NMS + max_per_image cap.
+        Returns (det [n,6] = x1,y1,x2,y2,score,class; plan) after one stream sync."""
+        plan = self._run(image, im_info, post=True, detect=True, orig_hw=orig_hw)
+        torch.cuda.current_stream().synchronize()
+        n = int(plan.ndet.item())
+        return plan.det[:n].cpu().numpy(), plan
