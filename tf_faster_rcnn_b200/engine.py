@@ -69,7 +69,8 @@ class Tape:
     def __init__(self, weights):
         self.w = weights
         self.steps = []        # (label, callable)
-        self.flops = 0.0       # algorithmic 2*MAC of conv/FC layers recorded
+        self.flops = 0.0       # algorithmic 2*MAC of every conv/FC layer recorded
+        self.conv_flops = 0.0  # ... of the tcgen05 implicit-GEMM launches only
         self.bufs = []
 
     def new(self, *shape, dtype=torch.float32):
@@ -92,7 +93,9 @@ class Tape:
         out = self.new(n, ho, wo, pc.cout)
         plan = ops.ConvPlan(x, pc, out, stride, pt, pl, act, residual)
         self.add("conv:" + name, plan.run)
-        self.flops += 2.0 * n * ho * wo * pc.cout * pc.kh * pc.kw * pc.cin
+        fl = 2.0 * n * ho * wo * pc.cout * pc.kh * pc.kw * pc.cin
+        self.flops += fl
+        self.conv_flops += fl
         return out
 
     def fc(self, x2d, name, act=N.ACT_NONE, packed=None):
