@@ -149,8 +149,19 @@ def run_ours(args):
     net.load_weights(weights)
     im_info = np.array([H, W, 1.0], np.float32)
     host_blob = torch.from_numpy(blob).pin_memory()
+    if args.ncu:
+        net.use_cuda_graph = False
     plan = net.plan_for(H, W)
     plan.image.copy_(host_blob)
+    if args.ncu:
+        plan.launch(1.0, H, W, post=True, detect=True)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        plan.launch(1.0, H, W, post=True, detect=True)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        print("ncu pass done: %d tape steps + 4 post launches" % len(plan.tape.steps))
+        return
     rec_bytes = plan.det.numel() * 4 + 4
     gathered = [torch.empty_like(plan.det) for _ in range(world)] if world > 1 else None
     gathered_n = [torch.empty_like(plan.ndet) for _ in range(world)] if world > 1 else None
@@ -264,6 +275,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--net", default="res101", choices=sorted(NETS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ncu", action="store_true", help="profiling aid: eager launches (no CUDA graph), one warm-up image, then ONE image "
+                    "between cudaProfilerStart/Stop (run under `ncu --profile-from-start off`); prints no bench line")
     args = ap.parse_args()
     if args.impl == "reference":
         if args.steps > 6:

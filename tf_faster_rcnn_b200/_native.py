@@ -37,6 +37,7 @@ SIGNATURES = {
     "frcnn_conv_plan_create": (ci, [C.POINTER(vp), C.POINTER(ConvDesc)]),
     "frcnn_conv_plan_run": (ci, [vp, vp]),
     "frcnn_conv_plan_info": (ci, [vp, ip, ip, ip, ip, ip, ip, ip, ip]),
+    "frcnn_conv_plan_set_trace": (ci, [vp, vp]),
     "frcnn_conv_plan_destroy": (None, [vp]),
     "frcnn_pack_conv_weights": (ci, [vp, vp, vp, ci, ci, ci, ci, vp]),
     "frcnn_conv_first": (ci, [vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp]),

@@ -9,22 +9,32 @@
 // Data movement: activations stay plain NHWC fp32 in HBM.  For filter tap (r,s) the A operand of a tile of
 // tn x th x tw output pixels is ONE 4-D TMA box {32 ch, tw, th, tn} of the input at offset
 // (w0*stride+s-pad_l, h0*stride+r-pad_t): out-of-bounds rows/cols are zero-filled by TMA, which IS the
-// convolution's zero padding -- no im2col buffer ever exists.  The box lands as <=128 rows x 128 B with
-// SWIZZLE_128B, exactly the K-major UMMA operand layout.  Weights are pre-split (hi/lo planes) and K-major.
+// convolution's zero padding -- no im2col buffer ever exists.  Weights are pre-split (hi/lo planes), K-major,
+// SWIZZLE_128B in shared memory (the UMMA B operand).
 //
-// Accumulation: the tensor core adds into its fp32 accumulator with truncation (measured: error grows
-// linearly with the number of MMA steps, ~2.4e-5 relative at K=3136), so accumulation is two-level: TMEM holds
-// only the partial sum of a short chunk of k-blocks (double buffered), which the epilogue warps add into fp32
-// REGISTER accumulators with round-to-nearest adds while the MMA warp works on the other TMEM buffer.
+// r01 finding 1 (profiles/r01_*): with both operands in shared memory the kernel was bound by the shared-memory
+// data pipe (3 MMAs re-read A and B, the splitter rewrote A twice: ~190 KB of smem traffic per 32-wide k-block,
+// l1tex data pipe ~90% busy, tensor pipe 23-56%).  So the A operand now lives in TENSOR MEMORY: the splitter
+// warps read the raw fp32 tile from smem once (un-swizzling their own 128-byte row), and tcgen05.st the hi and
+// lo planes into a 4-deep TMEM ring; tcgen05.mma runs in TS mode (A from TMEM, B from smem).
+// r01 finding 2: the tensor core adds into its fp32 accumulator with truncation (error grows linearly with the
+// number of MMA steps, ~2.4e-5 relative at K=3136), so accumulation is two-level: TMEM holds only the partial
+// sum of a short chunk of k-blocks (double buffered), which the epilogue warps add into fp32 REGISTER
+// accumulators with round-to-nearest adds.  r01 finding 3: every such promotion stalls the tensor pipe for ~950
+// cycles (tcgen05.ld of a 128x128 fp32 tile vs the MMAs' own TMEM traffic; independent of warp placement and of
+// code shape), so the chunk length trades accuracy for speed: 1/2/4/8 k-blocks -> 6e-7/7e-7/1.0e-6/1.9e-6 error
+// vs fp64 (the fp32 CPU reference sits at 0.6e-6..2e-6) for +37%/+20%/+9%/+5% time.  Default 4.
 //
-// Warp roles (320 threads, 1 CTA/SM):
-//   warp 0      TMA producer            full[s]  <- tx bytes
-//   warps 2..5  operand splitter        wait full[s]; A -> (A_hi in place, A_lo) in smem; fence.proxy.async;
-//                                       arrive ready[s]           (elementwise => swizzle-agnostic)
-//   warp 1      MMA issuer (1 thread)   wait ready[s]; 4 k-slices x 3 tcgen05.mma; tcgen05.commit -> empty[s];
-//                                       per chunk: wait tmem_empty[b] ... commit -> tmem_full[b]
-//   warps 6..9  accumulate + epilogue   per chunk: wait tmem_full[b]; tcgen05.ld; acc += partial; arrive
-//                                       tmem_empty[b]; finally y = act(acc*scale + shift (+res)); st.global
+// Warp roles (320 threads, 1 CTA/SM), rings are 4 deep (index kb & 3).  The MMA issuer is the HIGHEST warp id of its
+// scheduler partition on purpose: the arbiter favours high warp ids, and with the issuer at warp 1 the epilogue's
+// burst of tcgen05.ld + FADDs delayed every chunk hand-over by ~900 cycles (profiles/r01 trace).
+//   warp 8      TMA producer      A: wait a_empty[s] -> a_full[s];  B: wait mma_done[s] -> full[s] (tx)
+//   warps 0..3  operand splitter  wait a_full[s], mma_done[s]; smem row -> hi/lo -> tcgen05.st; arrive a_empty[s], full[s]
+//   warp 9      MMA issuer        wait full[s] (B landed + A stored); 4 k-slices x 3 tcgen05.mma (TS); commit -> mma_done[s];
+//                                 per chunk: wait tmem_empty[b] first
+//   warps 4..7  accumulate+epilogue  per chunk: wait mma_done[last k-block]; tcgen05.ld; acc += partial; arrive tmem_empty[b];
+//                                 finally y = act(acc*scale + shift (+res)); st.global
+// TMEM map (512 columns): [0, 2*BN) two accumulator buffers; [256, 512) A ring: slot s = 32 cols hi + 32 cols lo.
 #include "common.cuh"
 #include "../../include/frcnn_b200.h"
 #include <stdlib.h>
@@ -38,6 +48,9 @@ constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 4;  // 16 KiB
 constexpr int NUM_THREADS = 320;
 constexpr int SPLIT_THREADS = 128;
 constexpr int EPI_THREADS = 128;
+constexpr int RING = 4;                              // depth of the A-raw, B and TMEM-A rings
+constexpr int TMEM_COLS = 512;
+constexpr int TMEM_A_COL0 = 256;
 
 struct ConvKernelParams {
   float* out;
@@ -51,15 +64,20 @@ struct ConvKernelParams {
   int act;
   int a_box_bytes;
   int kb_per_chunk;   // k-blocks accumulated in TMEM before promotion to registers
+  long long* trace;   // debug: clock64() stamps of CTA (0,0)'s pipeline hand-offs; normally NULL
 };
 
-template <int BN> struct StageCfg;
-template <> struct StageCfg<128> { static constexpr int kStages = 3; };
-template <> struct StageCfg<64> { static constexpr int kStages = 4; };
-template <> struct StageCfg<32> { static constexpr int kStages = 5; };
+#define FRCNN_TRACE2(base, idx)                                                             \
+  do {                                                                                      \
+    if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && (idx) < 64) p.trace[(base) + (idx)] = clock64(); \
+  } while (0)
+#define FRCNN_TRACE(slot, kbv)                                                              \
+  do {                                                                                      \
+    if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && (kbv) < 64) p.trace[(kbv) * 8 + (slot)] = clock64(); \
+  } while (0)
 
-template <int BN> constexpr int stage_bytes() { return 2 * A_TILE_BYTES + 2 * BN * BLOCK_K * 4; }
-template <int BN> constexpr int smem_bytes() { return StageCfg<BN>::kStages * stage_bytes<BN>() + 1024 /*align slack*/ + 256 /*barriers*/; }
+template <int BN> constexpr int b_stage_bytes() { return 2 * BN * BLOCK_K * 4; }
+template <int BN> constexpr int smem_bytes() { return RING * (A_TILE_BYTES + b_stage_bytes<BN>()) + 1024 /*align slack*/ + 256 /*barriers*/; }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (8-row x 128 B atoms, 1024 B apart)
 __device__ __forceinline__ uint64_t sw128_desc(uint32_t saddr) {
@@ -76,17 +94,20 @@ template <int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
                         const __grid_constant__ CUtensorMap tmBlo, const ConvKernelParams p) {
-  constexpr int kStages = StageCfg<BN>::kStages;
-  constexpr int kStageBytes = stage_bytes<BN>();
   constexpr int kBTile = BN * BLOCK_K * 4;
+  constexpr int kBStage = b_stage_bytes<BN>();
   constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+  static_assert(2 * BN <= TMEM_A_COL0, "accumulator buffers overlap the TMEM A ring");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
-  uint64_t* ready = full + kStages;
-  uint64_t* empty = ready + kStages;
-  uint64_t* tmem_full = empty + kStages;      // [2]
+  uint8_t* smem_a = smem;                               // RING x 16 KiB raw fp32 A tiles (TMA, swizzled)
+  uint8_t* smem_b = smem + RING * A_TILE_BYTES;         // RING x (B_hi | B_lo)
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem_b + RING * kBStage);
+  uint64_t* a_empty = a_full + RING;
+  uint64_t* full = a_empty + RING;            // B bytes landed (tx) AND the 128 splitter threads stored A hi/lo
+  uint64_t* mma_done = full + RING;
+  uint64_t* tmem_full = mma_done + RING;      // [2]
   uint64_t* tmem_empty = tmem_full + 2;       // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
@@ -102,91 +123,120 @@ conv_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   const int nblk = blockIdx.y;
   const int num_kb = p.kh * p.kw * (p.cin / BLOCK_K);
   const int num_chunks = (num_kb + p.kb_per_chunk - 1) / p.kb_per_chunk;
+  // The completion of a chunk is the completion of its last k-block: the epilogue can wait on that k-block's
+  // mma_done barrier instead of a second tcgen05.commit, as long as the barrier cannot complete a second time before
+  // the epilogue looked (the MMA warp cannot start chunk c+2 before chunk c is drained): needs kb_per_chunk <= RING-1.
+  const bool chunk_by_mma_done = p.kb_per_chunk <= RING - 1;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmBhi); tma_prefetch_desc(&tmBlo);
-    for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&ready[s], SPLIT_THREADS); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < RING; ++s) {
+      mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], SPLIT_THREADS);
+      mbar_init(&full[s], SPLIT_THREADS + 1); mbar_init(&mma_done[s], 1);
+    }
     for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], EPI_THREADS); }
     mbar_fence_init();
   }
-  if (warp == 1) { tmem_alloc(tmem_slot, 2 * BN); tmem_relinquish(); }
+  if (warp == 8) { tmem_alloc(tmem_slot, TMEM_COLS); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
+  if (warp == 8) {
     if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
       const int cchunks = p.cin / BLOCK_K;
+      int kb = 0;
       for (int r = 0; r < p.kh; ++r)
         for (int s = 0; s < p.kw; ++s)
-          for (int kc = 0; kc < cchunks; ++kc) {
-            mbar_wait(&empty[stage], phase ^ 1);
-            uint8_t* st = smem + stage * kStageBytes;
-            mbar_expect_tx(&full[stage], (uint32_t)(p.a_box_bytes + 2 * kBTile));
-            tma_load_4d(st, &tmA, &full[stage], kc * BLOCK_K, w0 * p.stride + s - p.pad_l, h0 * p.stride + r - p.pad_t, n0);
+          for (int kc = 0; kc < cchunks; ++kc, ++kb) {
+            const int slot = kb & (RING - 1);
+            const uint32_t par = (uint32_t)(kb / RING) & 1u;
+            mbar_wait(&a_empty[slot], par ^ 1u);                 // splitter has consumed the raw tile
+            mbar_expect_tx(&a_full[slot], (uint32_t)p.a_box_bytes);
+            tma_load_4d(smem_a + slot * A_TILE_BYTES, &tmA, &a_full[slot], kc * BLOCK_K, w0 * p.stride + s - p.pad_l,
+                        h0 * p.stride + r - p.pad_t, n0);
+            mbar_wait(&mma_done[slot], par ^ 1u);                // MMAs that read this B slot have completed
+            FRCNN_TRACE(0, kb);
+            mbar_expect_tx(&full[slot], (uint32_t)(2 * kBTile));
             const int kcoord = ((r * p.kw + s) * p.cin) + kc * BLOCK_K;
-            tma_load_2d(st + 2 * A_TILE_BYTES, &tmBhi, &full[stage], kcoord, nblk * BN);
-            tma_load_2d(st + 2 * A_TILE_BYTES + kBTile, &tmBlo, &full[stage], kcoord, nblk * BN);
-            if (++stage == kStages) { stage = 0; phase ^= 1; }
+            tma_load_2d(smem_b + slot * kBStage, &tmBhi, &full[slot], kcoord, nblk * BN);
+            tma_load_2d(smem_b + slot * kBStage + kBTile, &tmBlo, &full[slot], kcoord, nblk * BN);
+            FRCNN_TRACE(1, kb);
           }
     }
     __syncwarp();
-  } else if (warp == 1) {
+  } else if (warp == 9) {
     if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      int kb = 0;
-      for (int c = 0; c < num_chunks; ++c) {
-        const int b = c & 1;
-        mbar_wait(&tmem_empty[b], ((uint32_t)(c >> 1) & 1u) ^ 1u);   // buffer drained by the epilogue warps
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(b * BN);
-        const int kb_end = min(num_kb, kb + p.kb_per_chunk);
-        bool first = true;
-        for (; kb < kb_end; ++kb) {
-          mbar_wait(&ready[stage], phase);
-          tc_fence_after();
-          const uint32_t sbase = smem_u32(smem + stage * kStageBytes);
-          const uint64_t a_hi = sw128_desc(sbase);
-          const uint64_t a_lo = sw128_desc(sbase + A_TILE_BYTES);
-          const uint64_t b_hi = sw128_desc(sbase + 2 * A_TILE_BYTES);
-          const uint64_t b_lo = sw128_desc(sbase + 2 * A_TILE_BYTES + kBTile);
-#pragma unroll
-          for (int k = 0; k < BLOCK_K / 8; ++k) {
-            const uint64_t off = (uint64_t)(k * 8 * 4) >> 4;   // advance 8 tf32 = 32 B inside the swizzle row
-            umma_tf32(tmem_d, a_lo + off, b_hi + off, kIdesc, first ? 0u : 1u);
-            first = false;
-            umma_tf32(tmem_d, a_hi + off, b_lo + off, kIdesc, 1u);
-            umma_tf32(tmem_d, a_hi + off, b_hi + off, kIdesc, 1u);
-          }
-          umma_commit(&empty[stage]);
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+      // one flat loop (chunk bookkeeping inline) so that the chunk hand-over runs the same, hot, instruction lines
+      int in_chunk = 0, c = 0;
+      uint32_t tmem_d = tmem_base;
+#pragma unroll 1
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int slot = kb & (RING - 1);
+        const uint32_t par = (uint32_t)(kb / RING) & 1u;
+        if (in_chunk == 0) {
+          const int b = c & 1;
+          mbar_wait(&tmem_empty[b], ((uint32_t)(c >> 1) & 1u) ^ 1u);   // buffer drained by the epilogue warps
+          tmem_d = tmem_base + (uint32_t)(b * BN);
+          FRCNN_TRACE2(576, c);
         }
-        umma_commit(&tmem_full[b]);
+        mbar_wait(&full[slot], par);
+        tc_fence_after();
+        FRCNN_TRACE(4, kb);
+        const uint32_t sb = smem_u32(smem_b + slot * kBStage);
+        const uint64_t b_hi = sw128_desc(sb);
+        const uint64_t b_lo = sw128_desc(sb + kBTile);
+        const uint32_t a_hi = tmem_base + (uint32_t)(TMEM_A_COL0 + slot * 64);
+        const uint32_t a_lo = a_hi + 32u;
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / 8; ++k) {
+          const uint64_t off = (uint64_t)(k * 8 * 4) >> 4;   // B: advance 8 tf32 = 32 B inside the swizzle row
+          const uint32_t ak = (uint32_t)(k * 8);             // A: 8 tf32 = 8 TMEM columns
+          umma_tf32_ts(tmem_d, a_lo + ak, b_hi + off, kIdesc, (k > 0 || in_chunk > 0) ? 1u : 0u);
+          umma_tf32_ts(tmem_d, a_hi + ak, b_lo + off, kIdesc, 1u);
+          umma_tf32_ts(tmem_d, a_hi + ak, b_hi + off, kIdesc, 1u);
+        }
+        umma_commit(&mma_done[slot]);
+        FRCNN_TRACE(5, kb);
+        if (++in_chunk == p.kb_per_chunk || kb + 1 == num_kb) {
+          if (!chunk_by_mma_done) umma_commit(&tmem_full[c & 1]);
+          in_chunk = 0; ++c;
+        }
       }
     }
     __syncwarp();
-  } else if (warp < 6) {
-    // ---------------- operand splitter ----------------
-    const int t = threadIdx.x - 64;
-    int stage = 0; uint32_t phase = 0;
+  } else if (warp < 4) {
+    // ---------------- operand splitter: smem raw tile row -> (hi, lo) planes in the TMEM A ring ----------------
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t lane_field = (uint32_t)(q * 32) << 16;
     for (int kb = 0; kb < num_kb; ++kb) {
-      mbar_wait(&full[stage], phase);
-      float4* a = reinterpret_cast<float4*>(smem + stage * kStageBytes);
-      float4* alo = reinterpret_cast<float4*>(smem + stage * kStageBytes + A_TILE_BYTES);
+      const int slot = kb & (RING - 1);
+      const uint32_t par = (uint32_t)(kb / RING) & 1u;
+      mbar_wait(&a_full[slot], par);
+      // SWIZZLE_128B: 16-byte chunk c of row r sits at chunk (c ^ (r & 7)); quarter-warp phases are conflict-free
+      const uint8_t* arow = smem_a + slot * A_TILE_BYTES + row * 128;
+      uint32_t hi[32], lo[32];
 #pragma unroll
-      for (int i = 0; i < A_TILE_BYTES / 16 / SPLIT_THREADS; ++i) {
-        const int idx = i * SPLIT_THREADS + t;
-        float4 v = a[idx], h, l;
-        h.x = to_tf32(v.x); h.y = to_tf32(v.y); h.z = to_tf32(v.z); h.w = to_tf32(v.w);
-        l.x = to_tf32(__fsub_rn(v.x, h.x)); l.y = to_tf32(__fsub_rn(v.y, h.y));
-        l.z = to_tf32(__fsub_rn(v.z, h.z)); l.w = to_tf32(__fsub_rn(v.w, h.w));
-        a[idx] = h; alo[idx] = l;
+      for (int c = 0; c < 8; ++c) {
+        const float4 v = *reinterpret_cast<const float4*>(arow + ((c ^ (row & 7)) << 4));
+        const float h0 = to_tf32(v.x), h1 = to_tf32(v.y), h2 = to_tf32(v.z), h3 = to_tf32(v.w);
+        hi[4 * c + 0] = __float_as_uint(h0); hi[4 * c + 1] = __float_as_uint(h1);
+        hi[4 * c + 2] = __float_as_uint(h2); hi[4 * c + 3] = __float_as_uint(h3);
+        lo[4 * c + 0] = __float_as_uint(to_tf32(__fsub_rn(v.x, h0))); lo[4 * c + 1] = __float_as_uint(to_tf32(__fsub_rn(v.y, h1)));
+        lo[4 * c + 2] = __float_as_uint(to_tf32(__fsub_rn(v.z, h2))); lo[4 * c + 3] = __float_as_uint(to_tf32(__fsub_rn(v.w, h3)));
       }
-      fence_proxy_async_smem();
-      mbar_arrive(&ready[stage]);
-      if (++stage == kStages) { stage = 0; phase ^= 1; }
+      mbar_arrive(&a_empty[slot]);                          // raw tile consumed (values are in registers)
+      mbar_wait(&mma_done[slot], par ^ 1u);                  // TMEM A slot no longer read by the tensor core
+      tc_fence_after();
+      const uint32_t ta = tmem_base + lane_field + (uint32_t)(TMEM_A_COL0 + slot * 64);
+      tmem_st_32x32(ta, hi);
+      tmem_st_32x32(ta + 32u, lo);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&full[slot]);
+      if (threadIdx.x == 0) FRCNN_TRACE(3, kb);
     }
   } else {
     // ---------------- accumulate (TMEM chunk partials -> fp32 registers, RN adds) ----------------
@@ -196,8 +246,14 @@ conv_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     for (int j = 0; j < BN; ++j) acc[j] = 0.f;
     for (int c = 0; c < num_chunks; ++c) {
       const int b = c & 1;
-      mbar_wait(&tmem_full[b], (uint32_t)(c >> 1) & 1u);
+      if (chunk_by_mma_done) {
+        const int kb_last = min(num_kb, (c + 1) * p.kb_per_chunk) - 1;
+        mbar_wait(&mma_done[kb_last & (RING - 1)], (uint32_t)(kb_last / RING) & 1u);
+      } else {
+        mbar_wait(&tmem_full[b], (uint32_t)(c >> 1) & 1u);
+      }
       tc_fence_after();
+      if (threadIdx.x == 128) FRCNN_TRACE(7, c);
 #pragma unroll
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t v[32];
@@ -208,6 +264,7 @@ conv_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       }
       tc_fence_before();
       mbar_arrive(&tmem_empty[b]);
+      if (threadIdx.x == 128) FRCNN_TRACE2(512, c);
     }
     // ---------------- epilogue ----------------
     const int row = q * 32 + lane;
@@ -251,7 +308,7 @@ conv_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 2 * BN); }
+  if (warp == 8) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -366,8 +423,9 @@ extern "C" int frcnn_conv_plan_create(frcnn_conv_plan** out, const frcnn_conv_de
       if (c > 32 && c / 2 >= d->cout) continue;        // tile mostly empty
       const long ctas = m_tiles * cdiv(d->cout, c);
       const long waves = (ctas + 147) / 148;
-      long per_kb = 6L * c; if (per_kb < 420) per_kb = 420;   // MMA cycles vs per-k-block floor (TMA/split/issue)
-      const long cost = waves * (num_kb * per_kb + 3000);
+      // measured (profiles/r01): a k-block costs ~1400 cycles whatever block_n is (SS-mode tcgen05.mma is bound by the
+      // 128-row A operand read for N <= 128), plus ~6000 cycles of prologue/drain per CTA => fewest waves wins, widest tile on ties
+      const long cost = waves * (num_kb * 1400L + 6000L);
       if (best < 0 || cost < best) { best = cost; bn = c; }
     }
   }
@@ -399,9 +457,10 @@ extern "C" int frcnn_conv_plan_create(frcnn_conv_plan** out, const frcnn_conv_de
   k.kh = d->kh; k.kw = d->kw; k.cin = d->cin; k.stride = d->stride; k.pad_t = d->pad_t; k.pad_l = d->pad_l;
   k.act = d->act;
   k.a_box_bytes = tn * th * tw * BLOCK_K * 4;
-  k.kb_per_chunk = d->kb_per_chunk > 0 ? d->kb_per_chunk : 2;
+  k.kb_per_chunk = d->kb_per_chunk > 0 ? d->kb_per_chunk : 4;
+  k.trace = nullptr;
   p->block_n = bn;
-  p->stages = bn == 128 ? StageCfg<128>::kStages : bn == 64 ? StageCfg<64>::kStages : StageCfg<32>::kStages;
+  p->stages = RING;
   p->smem = bn == 128 ? smem_bytes<128>() : bn == 64 ? smem_bytes<64>() : smem_bytes<32>();
   FRCNN_REQUIRE(m_tiles <= 0x7fffffffL, "too many tiles");
   p->grid = dim3((unsigned)m_tiles, (unsigned)cdiv(d->cout, bn), 1);
@@ -430,6 +489,12 @@ extern "C" int frcnn_conv_plan_info(const frcnn_conv_plan* p, int* block_n, int*
   if (grid_n) *grid_n = (int)p->grid.y;
   if (stages) *stages = p->stages;
   if (smem) *smem = p->smem;
+  return OK;
+}
+
+extern "C" int frcnn_conv_plan_set_trace(frcnn_conv_plan* p, long long* trace_dev) {
+  FRCNN_REQUIRE(p, "null plan");
+  p->kp.trace = trace_dev;
   return OK;
 }
 
