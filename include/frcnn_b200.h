@@ -91,13 +91,14 @@ typedef struct {
   int ho, wo;
   int act;                   /* FRCNN_ACT_* */
   int block_n;               /* 0 = choose; else 32/64/128 */
-  int kb_per_chunk;          /* 0 = default (4): 32-wide k-blocks summed in TMEM before promotion to registers */
+  int kb_per_chunk;          /* 0 = default (8): 32-wide k-blocks summed in TMEM before promotion to registers */
+  int split_k;               /* 0 = choose; 1 = never; n = split the K loop over n CTAs + deterministic reduce pass */
 } frcnn_conv_desc;
 
 int frcnn_conv_plan_create(frcnn_conv_plan** out, const frcnn_conv_desc* d);
 int frcnn_conv_plan_run(const frcnn_conv_plan* p, void* stream);
 int frcnn_conv_plan_info(const frcnn_conv_plan* p, int* block_n, int* tile_n, int* tile_h, int* tile_w,
-                         int* grid_m, int* grid_n, int* stages, int* smem_bytes);
+                         int* grid_m, int* grid_n, int* splits, int* smem_bytes);
 /* debug aid: trace_dev (int64[64*8], device) receives clock64() stamps of the pipeline hand-offs of CTA (0,0)
  * for its first 64 k-blocks: [kb][0]=producer saw slot free, [1]=TMA issued, [2]=splitter saw data, [6]=split done,
  * [3]=splitter arrived, [4]=MMA saw operands, [5]=MMAs issued+committed, [chunk][7]=epilogue saw TMEM chunk. NULL disables. */

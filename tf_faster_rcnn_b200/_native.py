@@ -24,7 +24,7 @@ class ConvDesc(C.Structure):
     _fields_ = [("in_dev", vp), ("w_hi_dev", vp), ("w_lo_dev", vp), ("scale_dev", vp), ("shift_dev", vp),
                 ("residual_dev", vp), ("out_dev", vp),
                 ("n", ci), ("h", ci), ("w", ci), ("cin", ci), ("cout", ci), ("kh", ci), ("kw", ci), ("stride", ci),
-                ("pad_t", ci), ("pad_l", ci), ("ho", ci), ("wo", ci), ("act", ci), ("block_n", ci), ("kb_per_chunk", ci)]
+                ("pad_t", ci), ("pad_l", ci), ("ho", ci), ("wo", ci), ("act", ci), ("block_n", ci), ("kb_per_chunk", ci), ("split_k", ci)]
 
 
 # name -> (restype, argtypes); must list every symbol of include/frcnn_b200.h (checked by tests/test_abi.py)

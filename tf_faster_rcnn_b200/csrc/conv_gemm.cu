@@ -22,8 +22,9 @@
 // sum of a short chunk of k-blocks (double buffered), which the epilogue warps add into fp32 REGISTER
 // accumulators with round-to-nearest adds.  r01 finding 3: every such promotion stalls the tensor pipe for ~950
 // cycles (tcgen05.ld of a 128x128 fp32 tile vs the MMAs' own TMEM traffic; independent of warp placement and of
-// code shape), so the chunk length trades accuracy for speed: 1/2/4/8 k-blocks -> 6e-7/7e-7/1.0e-6/1.9e-6 error
-// vs fp64 (the fp32 CPU reference sits at 0.6e-6..2e-6) for +37%/+20%/+9%/+5% time.  Default 4.
+// code shape), so the chunk length trades accuracy for speed (with all 12 MMAs of a k-block in one accumulator:
+// 1/2/4/8 k-blocks -> 6e-7/7e-7/1.0e-6/1.9e-6 error vs fp64, the fp32 CPU reference sitting at 0.6e-6..2e-6).  Hence
+// the D_main / D_small separation described at the TMEM map below, and a default chunk of 8 k-blocks.
 //
 // Warp roles (320 threads, 1 CTA/SM), rings are 4 deep (index kb & 3).  The MMA issuer is the HIGHEST warp id of its
 // scheduler partition on purpose: the arbiter favours high warp ids, and with the issuer at warp 1 the epilogue's
@@ -31,10 +32,13 @@
 //   warp 8      TMA producer      A: wait a_empty[s] -> a_full[s];  B: wait mma_done[s] -> full[s] (tx)
 //   warps 0..3  operand splitter  wait a_full[s], mma_done[s]; smem row -> hi/lo -> tcgen05.st; arrive a_empty[s], full[s]
 //   warp 9      MMA issuer        wait full[s] (B landed + A stored); 4 k-slices x 3 tcgen05.mma (TS); commit -> mma_done[s];
-//                                 per chunk: wait tmem_empty[b] first
-//   warps 4..7  accumulate+epilogue  per chunk: wait mma_done[last k-block]; tcgen05.ld; acc += partial; arrive tmem_empty[b];
+//                                 per chunk: wait acc_empty first, commit -> acc_full last
+//   warps 4..7  accumulate+epilogue  per chunk: wait acc_full; tcgen05.ld D_main; acc += partial; arrive acc_empty;
 //                                 finally y = act(acc*scale + shift (+res)); st.global
-// TMEM map (512 columns): [0, 2*BN) two accumulator buffers; [256, 512) A ring: slot s = 32 cols hi + 32 cols lo.
+// TMEM map (512 columns): [0, BN) D_main = chunk partial of the a_hi*b_hi products; [128, 128+BN) D_small = the two
+// cross terms a_lo*b_hi + a_hi*b_lo over the WHOLE k loop (2^-11 of the result, so its truncation is harmless and it is
+// read once per tile); [256, 512) A ring: slot s = 32 cols hi + 32 cols lo.  Only D_main is promoted per chunk, and it
+// takes 4 instead of 12 truncating adds per k-block, so the chunk can be 3x longer for the same error.
 #include "common.cuh"
 #include "../../include/frcnn_b200.h"
 #include <stdlib.h>
@@ -64,6 +68,9 @@ struct ConvKernelParams {
   int act;
   int a_box_bytes;
   int kb_per_chunk;   // k-blocks accumulated in TMEM before promotion to registers
+  int kb_per_split;   // split-K: blockIdx.z handles k-blocks [z*kb_per_split, ...); == total when not split
+  float* ws;          // split-K workspace [splits][out elements] (raw partial sums) or NULL
+  long long out_elems;
   long long* trace;   // debug: clock64() stamps of CTA (0,0)'s pipeline hand-offs; normally NULL
 };
 
@@ -97,7 +104,7 @@ conv_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   constexpr int kBTile = BN * BLOCK_K * 4;
   constexpr int kBStage = b_stage_bytes<BN>();
   constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
-  static_assert(2 * BN <= TMEM_A_COL0, "accumulator buffers overlap the TMEM A ring");
+  static_assert(BN <= 128, "D_main/D_small are 128 columns apart");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -107,9 +114,9 @@ conv_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   uint64_t* a_empty = a_full + RING;
   uint64_t* full = a_empty + RING;            // B bytes landed (tx) AND the 128 splitter threads stored A hi/lo
   uint64_t* mma_done = full + RING;
-  uint64_t* tmem_full = mma_done + RING;      // [2]
-  uint64_t* tmem_empty = tmem_full + 2;       // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* acc_full = mma_done + RING;       // D_main holds a finished chunk partial (tcgen05.commit)
+  uint64_t* acc_empty = acc_full + 1;         // the epilogue warps have read it (128 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -121,12 +128,10 @@ conv_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   const int tile_n = mt / (p.tiles_w * p.tiles_h);
   const int w0 = tile_w * p.tw, h0 = tile_h * p.th, n0 = tile_n * p.tn;
   const int nblk = blockIdx.y;
-  const int num_kb = p.kh * p.kw * (p.cin / BLOCK_K);
+  const int num_kb_total = p.kh * p.kw * (p.cin / BLOCK_K);
+  const int kb0 = blockIdx.z * p.kb_per_split;                  // split-K range of this CTA
+  const int num_kb = min(p.kb_per_split, num_kb_total - kb0);
   const int num_chunks = (num_kb + p.kb_per_chunk - 1) / p.kb_per_chunk;
-  // The completion of a chunk is the completion of its last k-block: the epilogue can wait on that k-block's
-  // mma_done barrier instead of a second tcgen05.commit, as long as the barrier cannot complete a second time before
-  // the epilogue looked (the MMA warp cannot start chunk c+2 before chunk c is drained): needs kb_per_chunk <= RING-1.
-  const bool chunk_by_mma_done = p.kb_per_chunk <= RING - 1;
 
   if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmBhi); tma_prefetch_desc(&tmBlo);
@@ -134,7 +139,7 @@ conv_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], SPLIT_THREADS);
       mbar_init(&full[s], SPLIT_THREADS + 1); mbar_init(&mma_done[s], 1);
     }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], EPI_THREADS); }
+    mbar_init(acc_full, 1); mbar_init(acc_empty, EPI_THREADS);
     mbar_fence_init();
   }
   if (warp == 8) { tmem_alloc(tmem_slot, TMEM_COLS); tmem_relinquish(); }
@@ -146,39 +151,38 @@ conv_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   if (warp == 8) {
     if (lane == 0) {
       const int cchunks = p.cin / BLOCK_K;
-      int kb = 0;
-      for (int r = 0; r < p.kh; ++r)
-        for (int s = 0; s < p.kw; ++s)
-          for (int kc = 0; kc < cchunks; ++kc, ++kb) {
-            const int slot = kb & (RING - 1);
-            const uint32_t par = (uint32_t)(kb / RING) & 1u;
-            mbar_wait(&a_empty[slot], par ^ 1u);                 // splitter has consumed the raw tile
-            mbar_expect_tx(&a_full[slot], (uint32_t)p.a_box_bytes);
-            tma_load_4d(smem_a + slot * A_TILE_BYTES, &tmA, &a_full[slot], kc * BLOCK_K, w0 * p.stride + s - p.pad_l,
-                        h0 * p.stride + r - p.pad_t, n0);
-            mbar_wait(&mma_done[slot], par ^ 1u);                // MMAs that read this B slot have completed
-            FRCNN_TRACE(0, kb);
-            mbar_expect_tx(&full[slot], (uint32_t)(2 * kBTile));
-            const int kcoord = ((r * p.kw + s) * p.cin) + kc * BLOCK_K;
-            tma_load_2d(smem_b + slot * kBStage, &tmBhi, &full[slot], kcoord, nblk * BN);
-            tma_load_2d(smem_b + slot * kBStage + kBTile, &tmBlo, &full[slot], kcoord, nblk * BN);
-            FRCNN_TRACE(1, kb);
-          }
+#pragma unroll 1
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int g = kb0 + kb;                                 // global k-block -> (filter tap, channel chunk)
+        const int tap = g / cchunks, kc = g - tap * cchunks;
+        const int r = tap / p.kw, s = tap - r * p.kw;
+        const int slot = kb & (RING - 1);
+        const uint32_t par = (uint32_t)(kb / RING) & 1u;
+        mbar_wait(&a_empty[slot], par ^ 1u);                 // splitter has consumed the raw tile
+        mbar_expect_tx(&a_full[slot], (uint32_t)p.a_box_bytes);
+        tma_load_4d(smem_a + slot * A_TILE_BYTES, &tmA, &a_full[slot], kc * BLOCK_K, w0 * p.stride + s - p.pad_l,
+                    h0 * p.stride + r - p.pad_t, n0);
+        mbar_wait(&mma_done[slot], par ^ 1u);                // MMAs that read this B slot have completed
+        FRCNN_TRACE(0, kb);
+        mbar_expect_tx(&full[slot], (uint32_t)(2 * kBTile));
+        const int kcoord = tap * p.cin + kc * BLOCK_K;
+        tma_load_2d(smem_b + slot * kBStage, &tmBhi, &full[slot], kcoord, nblk * BN);
+        tma_load_2d(smem_b + slot * kBStage + kBTile, &tmBlo, &full[slot], kcoord, nblk * BN);
+        FRCNN_TRACE(1, kb);
+      }
     }
     __syncwarp();
   } else if (warp == 9) {
     if (lane == 0) {
       // one flat loop (chunk bookkeeping inline) so that the chunk hand-over runs the same, hot, instruction lines
       int in_chunk = 0, c = 0;
-      uint32_t tmem_d = tmem_base;
+      const uint32_t d_main = tmem_base, d_small = tmem_base + 128u;
 #pragma unroll 1
       for (int kb = 0; kb < num_kb; ++kb) {
         const int slot = kb & (RING - 1);
         const uint32_t par = (uint32_t)(kb / RING) & 1u;
         if (in_chunk == 0) {
-          const int b = c & 1;
-          mbar_wait(&tmem_empty[b], ((uint32_t)(c >> 1) & 1u) ^ 1u);   // buffer drained by the epilogue warps
-          tmem_d = tmem_base + (uint32_t)(b * BN);
+          mbar_wait(acc_empty, ((uint32_t)c & 1u) ^ 1u);           // previous chunk partial has been promoted
           FRCNN_TRACE2(576, c);
         }
         mbar_wait(&full[slot], par);
@@ -193,14 +197,14 @@ conv_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         for (int k = 0; k < BLOCK_K / 8; ++k) {
           const uint64_t off = (uint64_t)(k * 8 * 4) >> 4;   // B: advance 8 tf32 = 32 B inside the swizzle row
           const uint32_t ak = (uint32_t)(k * 8);             // A: 8 tf32 = 8 TMEM columns
-          umma_tf32_ts(tmem_d, a_lo + ak, b_hi + off, kIdesc, (k > 0 || in_chunk > 0) ? 1u : 0u);
-          umma_tf32_ts(tmem_d, a_hi + ak, b_lo + off, kIdesc, 1u);
-          umma_tf32_ts(tmem_d, a_hi + ak, b_hi + off, kIdesc, 1u);
+          umma_tf32_ts(d_small, a_lo + ak, b_hi + off, kIdesc, (k > 0 || kb > 0) ? 1u : 0u);
+          umma_tf32_ts(d_small, a_hi + ak, b_lo + off, kIdesc, 1u);
+          umma_tf32_ts(d_main, a_hi + ak, b_hi + off, kIdesc, (k > 0 || in_chunk > 0) ? 1u : 0u);
         }
         umma_commit(&mma_done[slot]);
         FRCNN_TRACE(5, kb);
         if (++in_chunk == p.kb_per_chunk || kb + 1 == num_kb) {
-          if (!chunk_by_mma_done) umma_commit(&tmem_full[c & 1]);
+          umma_commit(acc_full);
           in_chunk = 0; ++c;
         }
       }
@@ -245,70 +249,134 @@ conv_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
 #pragma unroll
     for (int j = 0; j < BN; ++j) acc[j] = 0.f;
     for (int c = 0; c < num_chunks; ++c) {
-      const int b = c & 1;
-      if (chunk_by_mma_done) {
-        const int kb_last = min(num_kb, (c + 1) * p.kb_per_chunk) - 1;
-        mbar_wait(&mma_done[kb_last & (RING - 1)], (uint32_t)(kb_last / RING) & 1u);
-      } else {
-        mbar_wait(&tmem_full[b], (uint32_t)(c >> 1) & 1u);
-      }
+      mbar_wait(acc_full, (uint32_t)c & 1u);
       tc_fence_after();
       if (threadIdx.x == 128) FRCNN_TRACE(7, c);
 #pragma unroll
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t v[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * BN + c0), v);
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 32; ++j) acc[c0 + j] = __fadd_rn(acc[c0 + j], __uint_as_float(v[j]));
       }
       tc_fence_before();
-      mbar_arrive(&tmem_empty[b]);
+      mbar_arrive(acc_empty);
       if (threadIdx.x == 128) FRCNN_TRACE2(512, c);
     }
+    // the cross terms of the whole k loop (complete: the last acc_full commit covered every MMA)
+#pragma unroll
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(128 + c0), v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc[c0 + j] = __fadd_rn(acc[c0 + j], __uint_as_float(v[j]));
+    }
     // ---------------- epilogue ----------------
+    // r01 finding 4: writing each thread's own output row straight from registers (32 lanes = 32 rows, 8 KB apart) made
+    // every global access 32 separate sectors and cost ~20 us per CTA.  The tile is therefore transposed through the
+    // (now idle) A-raw ring: thread = row writes its BN values as XOR-swizzled 16-byte chunks (conflict free), then
+    // each lane owns 4 fixed output channels and walks the warp's 32 rows with fully coalesced 128-bit accesses.
+    constexpr int CH = BN / 4;                              // 16-byte chunks per row
+    float4* stage = reinterpret_cast<float4*>(smem_a + q * (32 * BN * 4));
+#pragma unroll
+    for (int j = 0; j < CH; ++j)
+      stage[lane * CH + ((j ^ lane) & (CH - 1))] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+    // pixel offset of this thread's row (shuffled to the lanes that write it)
     const int row = q * 32 + lane;
     const int rows_img = p.th * p.tw;
     const int dn = row / rows_img, rem = row % rows_img;
     const int dh = rem / p.tw, dw = rem % p.tw;
     const int n = n0 + dn, h = h0 + dh, w = w0 + dw;
     const bool valid = (row < p.tn * rows_img) && n < p.nimg && h < p.ho && w < p.wo;
-    if (valid) {
-      const size_t pix = ((size_t)n * p.ho + h) * p.wo + w;
-      float* orow = p.out + pix * p.cout;
-      const float* rrow = p.residual ? p.residual + pix * p.cout : nullptr;
-      const bool vec_ok = (p.cout & 3) == 0;
+    const long long my_pix = valid ? (((long long)n * p.ho + h) * p.wo + w) : -1;
+    __syncwarp();
+    constexpr int ROWS_PER_IT = 32 / CH;                    // 1 for BN=128, 2 for BN=64, 4 for BN=32
+    const int cg = lane % CH;                               // column group of this lane
+    const int rsub = lane / CH;
+    const int c = nblk * BN + cg * 4;                       // first of this lane's 4 output channels
+    const bool vec_ok = (p.cout & 3) == 0;
+    const bool raw = p.ws != nullptr;                       // split-K: plain partial sums, epilogue runs in the reduce kernel
+    float* const obase = raw ? p.ws + (size_t)blockIdx.z * p.out_elems : p.out;
+    const float* const rbase = raw ? nullptr : p.residual;
+    const float* const scale = raw ? nullptr : p.scale;
+    const float* const shift = raw ? nullptr : p.shift;
+    const int act = raw ? FRCNN_ACT_NONE : p.act;
+    float sc[4] = {1.f, 1.f, 1.f, 1.f}, sh[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int j = 0; j < BN; j += 4) {
-        const int c = nblk * BN + j;
-        if (c < p.cout) {
-          float y[4];
+    for (int e = 0; e < 4; ++e)
+      if (c + e < p.cout) {
+        if (scale) sc[e] = __ldg(scale + c + e);
+        if (shift) sh[e] = __ldg(shift + c + e);
+      }
+#pragma unroll 4
+    for (int it = 0; it < 32 / ROWS_PER_IT; ++it) {
+      const int r = it * ROWS_PER_IT + rsub;
+      const long long pix = __shfl_sync(0xffffffffu, my_pix, r);
+      if (pix < 0 || c >= p.cout) continue;
+      const float4 v = stage[r * CH + ((cg ^ r) & (CH - 1))];
+      float y[4] = {v.x, v.y, v.z, v.w};
+      float* optr = obase + (size_t)pix * p.cout + c;
+      float res[4] = {0.f, 0.f, 0.f, 0.f};
+      if (rbase) {
+        const float* rptr = rbase + (size_t)pix * p.cout + c;
+        if (vec_ok) { const float4 rv = __ldg(reinterpret_cast<const float4*>(rptr)); res[0] = rv.x; res[1] = rv.y; res[2] = rv.z; res[3] = rv.w; }
+        else {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            float a = acc[j + e];
-            const int ce = c + e;
-            if (ce < p.cout) {
-              if (p.scale) a = __fmul_rn(a, __ldg(p.scale + ce));
-              if (p.shift) a = __fadd_rn(a, __ldg(p.shift + ce));
-              if (rrow) a = __fadd_rn(a, __ldg(rrow + ce));
-              if (p.act == FRCNN_ACT_RELU) a = fmaxf(a, 0.f);
-              else if (p.act == FRCNN_ACT_RELU6) a = fminf(fmaxf(a, 0.f), 6.f);
-            }
-            y[e] = a;
-          }
-          if (vec_ok) {
-            *reinterpret_cast<float4*>(orow + c) = make_float4(y[0], y[1], y[2], y[3]);
-          } else {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) if (c + e < p.cout) orow[c + e] = y[e];
-          }
+          for (int e = 0; e < 4; ++e) if (c + e < p.cout) res[e] = __ldg(rptr + e);
         }
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float a = y[e];
+        if (scale) a = __fmul_rn(a, sc[e]);
+        if (shift) a = __fadd_rn(a, sh[e]);
+        if (rbase) a = __fadd_rn(a, res[e]);
+        if (act == FRCNN_ACT_RELU) a = fmaxf(a, 0.f);
+        else if (act == FRCNN_ACT_RELU6) a = fminf(fmaxf(a, 0.f), 6.f);
+        y[e] = a;
+      }
+      if (vec_ok) {
+        *reinterpret_cast<float4*>(optr) = make_float4(y[0], y[1], y[2], y[3]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) if (c + e < p.cout) optr[e] = y[e];
       }
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 8) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
+}
+
+// split-K second pass: out = act((sum_z ws[z]) * scale + shift (+ residual)), z summed in index order (deterministic)
+__global__ void splitk_reduce_kernel(const float* __restrict__ ws, int splits, long long out_elems, int cout,
+                                     const float* __restrict__ scale, const float* __restrict__ shift,
+                                     const float* __restrict__ residual, int act, float* __restrict__ out) {
+  const long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // one float4 (cout % 4 == 0) per thread
+  const long long i = i4 * 4;
+  if (i >= out_elems) return;
+  float4 a = __ldg(reinterpret_cast<const float4*>(ws + i));
+  for (int z = 1; z < splits; ++z) {
+    const float4 b = __ldg(reinterpret_cast<const float4*>(ws + (size_t)z * out_elems + i));
+    a.x = __fadd_rn(a.x, b.x); a.y = __fadd_rn(a.y, b.y); a.z = __fadd_rn(a.z, b.z); a.w = __fadd_rn(a.w, b.w);
+  }
+  const int c = (int)(i % cout);
+  float y[4] = {a.x, a.y, a.z, a.w};
+  float r4[4] = {0.f, 0.f, 0.f, 0.f};
+  if (residual) { const float4 rv = __ldg(reinterpret_cast<const float4*>(residual + i)); r4[0] = rv.x; r4[1] = rv.y; r4[2] = rv.z; r4[3] = rv.w; }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    float v = y[e];
+    if (scale) v = __fmul_rn(v, __ldg(scale + c + e));
+    if (shift) v = __fadd_rn(v, __ldg(shift + c + e));
+    if (residual) v = __fadd_rn(v, r4[e]);
+    if (act == FRCNN_ACT_RELU) v = fmaxf(v, 0.f);
+    else if (act == FRCNN_ACT_RELU6) v = fminf(fmaxf(v, 0.f), 6.f);
+    y[e] = v;
+  }
+  *reinterpret_cast<float4*>(out + i) = make_float4(y[0], y[1], y[2], y[3]);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -357,6 +425,12 @@ struct frcnn_conv_plan {
   ConvKernelParams kp;
   int block_n, stages, smem;
   dim3 grid;
+  int splits;
+  float* ws;               // owned split-K workspace
+  // reduce-pass arguments (the GEMM pass sees NULL epilogue inputs when split)
+  const float *scale, *shift, *residual;
+  float* out;
+  int act;
 };
 
 // choose the tile of output pixels (tn x th x tw <= 128) that needs the fewest tiles
@@ -390,6 +464,12 @@ static int launch(const frcnn_conv_plan* p, cudaStream_t st) {
   }
   conv_gemm_tf32x3_kernel<BN><<<p->grid, NUM_THREADS, smem_bytes<BN>(), st>>>(p->tmA, p->tmBhi, p->tmBlo, p->kp);
   FRCNN_LAUNCH_CHECK();
+  if (p->splits > 1) {
+    const long long n4 = p->kp.out_elems / 4;
+    splitk_reduce_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(p->ws, p->splits, p->kp.out_elems, p->kp.cout, p->scale, p->shift,
+                                                                      p->residual, p->act, p->out);
+    FRCNN_LAUNCH_CHECK();
+  }
   return OK;
 }
 
@@ -457,13 +537,39 @@ extern "C" int frcnn_conv_plan_create(frcnn_conv_plan** out, const frcnn_conv_de
   k.kh = d->kh; k.kw = d->kw; k.cin = d->cin; k.stride = d->stride; k.pad_t = d->pad_t; k.pad_l = d->pad_l;
   k.act = d->act;
   k.a_box_bytes = tn * th * tw * BLOCK_K * 4;
-  k.kb_per_chunk = d->kb_per_chunk > 0 ? d->kb_per_chunk : 4;
+  k.kb_per_chunk = d->kb_per_chunk > 0 ? d->kb_per_chunk : 8;
   k.trace = nullptr;
+  k.out_elems = (long long)d->n * d->ho * d->wo * d->cout;
+  // split-K (deterministic two-pass) when the output tiling alone leaves most of the 148 SMs idle
+  const long ctas = m_tiles * cdiv(d->cout, bn);
+  int splits = d->split_k;
+  if (splits == 0) {
+    splits = 1;
+    if (ctas <= 74 && num_kb >= 16 && (d->cout & 3) == 0) {
+      splits = (int)(148 / ctas);
+      if (splits > num_kb / 8) splits = num_kb / 8;
+      if (splits > 8) splits = 8;
+      if (splits < 1) splits = 1;
+    }
+  }
+  FRCNN_REQUIRE(splits >= 1 && splits <= 64 && (splits == 1 || (d->cout & 3) == 0), "bad split_k");
+  int kbs = cdiv(num_kb, splits);
+  kbs = cdiv(kbs, k.kb_per_chunk) * k.kb_per_chunk;        // whole chunks per split
+  splits = cdiv(num_kb, kbs);
+  k.kb_per_split = kbs;
+  k.ws = nullptr;
+  p->splits = splits; p->ws = nullptr;
+  p->scale = d->scale_dev; p->shift = d->shift_dev; p->residual = d->residual_dev; p->out = d->out_dev; p->act = d->act;
+  if (splits > 1) {
+    cudaError_t e = cudaMalloc(&p->ws, (size_t)splits * k.out_elems * sizeof(float));
+    if (e != cudaSuccess) { free(p); return cuda_fail(e, "split-K workspace", __FILE__, __LINE__); }
+    k.ws = p->ws;
+  }
   p->block_n = bn;
   p->stages = RING;
   p->smem = bn == 128 ? smem_bytes<128>() : bn == 64 ? smem_bytes<64>() : smem_bytes<32>();
   FRCNN_REQUIRE(m_tiles <= 0x7fffffffL, "too many tiles");
-  p->grid = dim3((unsigned)m_tiles, (unsigned)cdiv(d->cout, bn), 1);
+  p->grid = dim3((unsigned)m_tiles, (unsigned)cdiv(d->cout, bn), (unsigned)splits);
   *out = p;
   return OK;
 }
@@ -487,7 +593,7 @@ extern "C" int frcnn_conv_plan_info(const frcnn_conv_plan* p, int* block_n, int*
   if (tile_w) *tile_w = p->kp.tw;
   if (grid_m) *grid_m = (int)p->grid.x;
   if (grid_n) *grid_n = (int)p->grid.y;
-  if (stages) *stages = p->stages;
+  if (stages) *stages = p->splits;   /* reported as "splits": the ring depth is a compile-time constant (4) */
   if (smem) *smem = p->smem;
   return OK;
 }
@@ -498,4 +604,7 @@ extern "C" int frcnn_conv_plan_set_trace(frcnn_conv_plan* p, long long* trace_de
   return OK;
 }
 
-extern "C" void frcnn_conv_plan_destroy(frcnn_conv_plan* p) { free(p); }
+extern "C" void frcnn_conv_plan_destroy(frcnn_conv_plan* p) {
+  if (p && p->ws) cudaFree(p->ws);
+  free(p);
+}

@@ -50,14 +50,14 @@ class PackedConv:
 class ConvPlan:
     """frcnn_conv_plan bound to fixed input/output/residual buffers (TMA descriptors hold raw pointers)."""
 
-    def __init__(self, x, pc, out, stride=1, pad_t=0, pad_l=0, act=N.ACT_NONE, residual=None, block_n=0, kb_per_chunk=0):
+    def __init__(self, x, pc, out, stride=1, pad_t=0, pad_l=0, act=N.ACT_NONE, residual=None, block_n=0, kb_per_chunk=0, split_k=0):
         _f32(x); _f32(out)
         n, h, w, cin = x.shape
         assert cin == pc.cin, (cin, pc.cin)
         no, ho, wo, co = out.shape
         assert no == n and co == pc.cout
         d = N.ConvDesc(_p(x), _p(pc.w_hi), _p(pc.w_lo), _p(pc.scale), _p(pc.shift), _p(residual), _p(out),
-                       n, h, w, cin, pc.cout, pc.kh, pc.kw, stride, pad_t, pad_l, ho, wo, act, block_n, kb_per_chunk)
+                       n, h, w, cin, pc.cout, pc.kh, pc.kw, stride, pad_t, pad_l, ho, wo, act, block_n, kb_per_chunk, split_k)
         self._h = C.c_void_p()
         N.check(N.lib().frcnn_conv_plan_create(C.byref(self._h), C.byref(d)), "conv_plan_create")
         self._keep = (x, pc, out, residual)
@@ -68,7 +68,7 @@ class ConvPlan:
     def info(self):
         v = [C.c_int() for _ in range(8)]
         N.check(N.lib().frcnn_conv_plan_info(self._h, *[C.byref(a) for a in v]), "conv_plan_info")
-        return dict(zip(["block_n", "tile_n", "tile_h", "tile_w", "grid_m", "grid_n", "stages", "smem"], [a.value for a in v]))
+        return dict(zip(["block_n", "tile_n", "tile_h", "tile_w", "grid_m", "grid_n", "splits", "smem"], [a.value for a in v]))
 
     def __del__(self):
         try:
