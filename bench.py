@@ -162,21 +162,19 @@ def run_ours(args):
         torch.cuda.profiler.stop()
         print("ncu pass done: %d tape steps + 4 post launches" % len(plan.tape.steps))
         return
+    from tf_faster_rcnn_b200 import parallel
     rec_bytes = plan.det.numel() * 4 + 4
-    gathered = [torch.empty_like(plan.det) for _ in range(world)] if world > 1 else None
-    gathered_n = [torch.empty_like(plan.ndet) for _ in range(world)] if world > 1 else None
+    gather = parallel.RecordGather(plan.det, plan.ndet, world)
 
     def step_resident():
         plan.launch(1.0, H, W, post=True, detect=True)
         if world > 1:                                   # one all-gather of the fixed-size records per step
-            dist.all_gather(gathered, plan.det)
-            dist.all_gather(gathered_n, plan.ndet)
+            gather.gather(plan.det, plan.ndet)
 
     def step_e2e():
         det, _ = net.detect(host_blob, im_info, (H, W))  # H2D blob, graph, post, D2H records (+ sync)
         if world > 1:
-            dist.all_gather(gathered, plan.det)
-            dist.all_gather(gathered_n, plan.ndet)
+            gather.gather(plan.det, plan.ndet)
         return det
 
     def barrier():

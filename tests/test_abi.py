@@ -1,0 +1,54 @@
+"""The C-ABI library loads without a GPU and exports every symbol include/frcnn_b200.h declares
+(no compute calls here)."""
+import ctypes
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "frcnn_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(frcnn_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported_and_bound():
+    from tf_faster_rcnn_b200 import _native
+    lib = ctypes.CDLL(_native.LIB_PATH)
+    names = declared_symbols()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), "symbol %s declared in the header is not exported" % n
+        assert n in _native.SIGNATURES, "symbol %s has no ctypes signature" % n
+    for n in _native.SIGNATURES:
+        assert n in names, "ctypes signature for undeclared symbol %s" % n
+
+
+def test_version_and_error_text_without_gpu():
+    from tf_faster_rcnn_b200 import _native
+    L = _native.lib()
+    assert L.frcnn_version() >= 100
+    import torch
+    if not torch.cuda.is_available():
+        rc = L.frcnn_check_device(0)
+        assert rc != 0 and "device" in _native.last_error().lower()      # fails loudly, no fallback
+        # argument validation does not need a device
+        rc = L.frcnn_conv_plan_create(None, None)
+        assert rc == -2 and _native.last_error()
+
+
+def test_conv_desc_struct_matches_header():
+    """field count/order of the ctypes mirror == the C struct (guards silent ABI drift)."""
+    from tf_faster_rcnn_b200 import _native
+    src = open(os.path.join(ROOT, "include", "frcnn_b200.h")).read()
+    body = re.search(r"typedef struct \{(.*?)\} frcnn_conv_desc;", src, flags=re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        decl = re.sub(r"^(const\s+)?(float\*|int)\s*", "", decl)
+        fields += [f.strip().lstrip("*") for f in decl.split(",")]
+    assert fields == [f[0] for f in _native.ConvDesc._fields_]

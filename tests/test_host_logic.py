@@ -1,0 +1,196 @@
+"""Host-side logic of the reference-facing surface (no GPU): config tree, blobs, anchors, thresholds, imdb,
+tensorflow shim, the N>1 record gather over gloo, and the reference's own tools/demo.py driven unchanged up to the
+(loud) device check."""
+import os
+import subprocess
+import sys
+import textwrap
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G = np.load(os.path.join(ROOT, "tests", "golden", "reference_vectors.npz"))
+REF = "/root/reference"
+
+
+def test_config_defaults_merge_and_set(tmp_path):
+    from model import config as C
+    cfg = C.cfg
+    assert cfg.TEST.SCALES == (600,) and cfg.TEST.MAX_SIZE == 1000 and cfg.TEST.NMS == 0.3
+    assert cfg.TEST.RPN_POST_NMS_TOP_N == 300 and cfg.TEST.RPN_NMS_THRESH == 0.7 and cfg.POOLING_SIZE == 7
+    assert cfg.USE_E2E_TF is True and cfg.USE_GPU_NMS is True and cfg.RPN_CHANNELS == 512
+    assert np.allclose(cfg.PIXEL_MEANS, [[[102.9801, 115.9465, 122.7717]]])
+    y = tmp_path / "x.yml"
+    y.write_text("EXP_DIR: t\nTEST:\n  HAS_RPN: True\n  SCALES: [800]\n  MAX_SIZE: 1333\nANCHOR_SCALES: [2,4,8,16,32]\n")
+    saved = (cfg.TEST.SCALES, cfg.TEST.MAX_SIZE, list(cfg.ANCHOR_SCALES), cfg.EXP_DIR, cfg.TEST.HAS_RPN)
+    try:
+        C.cfg_from_file(str(y))
+        assert cfg.TEST.SCALES == (800,) and cfg.TEST.MAX_SIZE == 1333 and cfg.ANCHOR_SCALES == [2, 4, 8, 16, 32]
+        C.cfg_from_list(["TEST.MODE", "top", "TEST.RPN_TOP_N", "1000"])
+        assert cfg.TEST.MODE == "top" and cfg.TEST.RPN_TOP_N == 1000
+        with pytest.raises(KeyError):
+            C._merge({"NOPE": 1}, cfg)
+        with pytest.raises(ValueError):
+            C._merge({"TEST": {"NMS": "x"}}, cfg)
+        with pytest.raises(AssertionError):
+            C.cfg_from_list(["TEST.NMS", "'str'"])
+
+        class Imdb:
+            name = "unit"
+        old_root = cfg.ROOT_DIR
+        cfg.ROOT_DIR = str(tmp_path)
+        d = C.get_output_dir(Imdb(), None)
+        assert d.endswith(os.path.join("output", "t", "unit", "default")) and os.path.isdir(d)
+        cfg.ROOT_DIR = old_root
+    finally:
+        cfg.TEST.SCALES, cfg.TEST.MAX_SIZE, cfg.ANCHOR_SCALES, cfg.EXP_DIR, cfg.TEST.HAS_RPN = saved
+        cfg.TEST.MODE, cfg.TEST.RPN_TOP_N = "nms", 5000
+
+
+def test_im_list_to_blob_matches_reference_vector():
+    from utils.blob import im_list_to_blob
+    out = im_list_to_blob([G["blob_in0"], G["blob_in1"]])
+    assert out.dtype == np.float32 and np.array_equal(out, G["blob_out"])
+
+
+@pytest.mark.parametrize("tag,scales", [("s3", (8, 16, 32)), ("s4", (4, 8, 16, 32)), ("s5", (2, 4, 8, 16, 32))])
+def test_product_anchors_match_reference(tag, scales):
+    from layer_utils.generate_anchors import generate_anchors
+    from layer_utils.snippets import generate_anchors_pre
+    from oracle import anchors as OA
+    assert np.array_equal(generate_anchors(scales=np.array(scales)), G["anchors_" + tag])
+    tab, n = generate_anchors_pre(5, 7, 16, scales, (0.5, 1, 2))
+    assert n == 5 * 7 * 3 * len(scales) and np.array_equal(tab, OA.tiled_anchors(5, 7, 16, scales, (0.5, 1, 2)))
+
+
+def test_image_blob_scaling_rule_matches_oracle():
+    from model.test import _get_image_blob
+    from oracle import pipeline as P
+    rng = np.random.default_rng(0)
+    for hw in ((375, 500), (480, 640), (300, 1200), (1000, 200)):
+        im = rng.integers(0, 256, hw + (3,), dtype=np.uint8)
+        blob, scales = _get_image_blob(im)
+        want, s = P.get_image_blob(im)
+        assert scales.shape == (1,) and scales[0] == s and np.array_equal(blob, want)
+        assert max(blob.shape[1:3]) <= 1000 + 1
+
+
+def test_nms_threshold_rule_and_empty_input():
+    from tf_faster_rcnn_b200 import engine, _native as N
+    from model.nms_wrapper import nms
+    t, f = engine.nms_threshold(0.3, use_gpu_nms=False)
+    assert f == N.NMS_MODE_CPU_NMS and t >= 0.3 and np.float32(t) == np.nextafter(np.float32(0.3), np.float32(0)) or t >= 0.3
+    t2, f2 = engine.nms_threshold(0.3, use_gpu_nms=True)
+    assert f2 == N.NMS_MODE_GPU_NMS and t2 == float(np.float32(0.3))
+    assert engine.nms_threshold(0.5, False)[0] == 0.5
+    assert nms(np.zeros((0, 5), np.float32), 0.3) == []          # nms_wrapper.py:18-19, no device needed
+
+
+def test_conv_geometry_helpers():
+    from tf_faster_rcnn_b200 import ops
+    assert ops.same_pads(600, 3, 1) == (1, 1) and ops.same_pads(75, 2, 2) == (0, 1) and ops.same_pads(38, 2, 2) == (0, 0)
+    assert ops.conv_out_hw(600, 800, 7, 2, "EXPLICIT") == (300, 400, 3, 3)
+    assert ops.conv_out_hw(75, 100, 3, 2, "EXPLICIT") == (38, 50, 1, 1)
+    assert ops.conv_out_hw(38, 50, 3, 1, "SAME") == (38, 50, 1, 1)
+
+
+def test_synthetic_imdb_and_tf_shim(tmp_path):
+    from datasets.factory import get_imdb
+    imdb = get_imdb("synthetic_3_5")
+    assert imdb.num_classes == 5 and len(imdb.image_index) == 3 and os.path.isfile(imdb.image_path_at(2))
+    with pytest.raises(KeyError):
+        get_imdb("voc_2007_test")
+    from tf_faster_rcnn_b200 import paths
+    sys.path.append(paths.SHIMS)
+    try:
+        import importlib
+        tf = importlib.import_module("tensorflow")
+        c = tf.ConfigProto(allow_soft_placement=True)
+        c.gpu_options.allow_growth = True
+        s = tf.Session(config=c)
+        with pytest.raises(IOError):
+            tf.train.Saver().restore(s, str(tmp_path / "missing.ckpt"))
+        s.close()
+    finally:
+        sys.path.remove(paths.SHIMS)
+        sys.modules.pop("tensorflow", None)
+
+
+GLOO_WORKER = textwrap.dedent("""
+    import os, sys
+    sys.path.insert(0, %r)
+    import numpy as np, torch, torch.distributed as dist
+    from tf_faster_rcnn_b200 import parallel as PP
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    num_images, C, max_det = 5, 4, 8
+    all_boxes = [[[] for _ in range(num_images)] for _ in range(C)]
+    det = torch.zeros(max_det, 6); ndet = torch.zeros(1, dtype=torch.int32)
+    g = PP.RecordGather(det, ndet, world)
+    mine = PP.shard_indices(num_images, rank, world)
+    for step in range(PP.steps_for(num_images, world)):
+        det.zero_(); ndet.zero_()
+        if step < len(mine):
+            img = mine[step]
+            n = 1 + img %% 3
+            for k in range(n):
+                det[k] = torch.tensor([img, k, img + 10, k + 10, 0.9 - 0.1 * k, 1 + (img + k) %% (C - 1)], dtype=torch.float32)
+            ndet[0] = n
+        d, nn = g.gather(det, ndet)
+        PP.records_to_all_boxes(all_boxes, step, world, d, nn, num_images)
+    tot = sum(len(all_boxes[j][i]) for j in range(1, C) for i in range(num_images))
+    assert tot == sum(1 + i %% 3 for i in range(num_images)), tot
+    for i in range(num_images):
+        for j in range(1, C):
+            for row in all_boxes[j][i]:
+                assert row[0] == i
+    dist.destroy_process_group()
+    print("rank", rank, "ok")
+""")
+
+
+def test_two_rank_record_gather_over_gloo(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(GLOO_WORKER % ROOT)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29611", WORLD_SIZE="2")
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r)), stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+             for r in range(2)]
+    outs = [p.communicate(timeout=180)[0].decode() for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert all("ok" in o for o in outs)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree only exists in the authoring container")
+def test_reference_demo_script_drives_this_lib_unchanged(tmp_path):
+    """Runs the reference's OWN tools/demo.py (unmodified, in place) against this repo's lib/ + shims.  Without a GPU it
+    must get through argument parsing, cfg, tf.Session, create_architecture, Saver.restore and cv2.imread, and stop at the
+    first image with the loud 'no CUDA device' error -- there is no CPU fallback to fall into."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CPU-container check")
+    ck = tmp_path / "output" / "res101" / "voc_2007_trainval+voc_2012_trainval" / "default"
+    ck.mkdir(parents=True)
+    pre = str(ck / "res101_faster_rcnn_iter_110000.ckpt")
+    subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "make_synthetic_ckpt.py"), "--net", "res50", "--classes", "21",
+                           "--anchors", "9", "--out", pre], cwd=ROOT)
+    code = textwrap.dedent("""
+        import sys, runpy, types
+        sys.modules["_init_paths"] = types.ModuleType("_init_paths")   # the reference's own file would add ITS lib/ (INTEGRATION.md)
+        sys.path.insert(0, %r)
+        from tf_faster_rcnn_b200 import paths
+        paths.add_lib_path(with_shims=True)
+        from model.config import cfg
+        cfg.DATA_DIR = %r
+        import nets.resnet_v1 as R
+        _orig = R.resnetv1.__init__
+        R.resnetv1.__init__ = lambda self, num_layers=50: _orig(self, 50)   # keep the synthetic checkpoint small
+        sys.argv = ["demo.py", "--net", "res101", "--dataset", "pascal_voc_0712"]
+        runpy.run_path(%r, run_name="__main__")
+    """) % (ROOT, os.path.join(REF, "data"), os.path.join(REF, "tools", "demo.py"))
+    r = subprocess.run([sys.executable, "-c", code], cwd=str(tmp_path), capture_output=True, text=True, timeout=300)
+    out = r.stdout + r.stderr
+    assert r.returncode != 0
+    assert "Loaded network" in out, out[-2000:]
+    assert "Demo for data/demo/000456.jpg" in out, out[-2000:]
+    assert "check_device failed" in out and "no CUDA device" in out, out[-2000:]

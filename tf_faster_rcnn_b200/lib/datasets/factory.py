@@ -1,0 +1,73 @@
+"""`get_imdb(name)` (lib/datasets/factory.py:50-54).  The VOC/COCO loaders need datasets that are not available
+offline and are out of scope; this build registers image-directory and synthetic imdbs that satisfy exactly what
+test_net needs (lib/model/test.py:138-192): name, num_classes, image_index, image_path_at, evaluate_detections."""
+import os
+import pickle
+import tempfile
+
+import numpy as np
+
+_SETS = {}
+
+
+class SimpleImdb(object):
+    def __init__(self, name, image_paths, num_classes):
+        self._name = name
+        self._paths = list(image_paths)
+        self._classes = ["__background__"] + ["class_%d" % i for i in range(1, num_classes)]
+
+    name = property(lambda self: self._name)
+    num_classes = property(lambda self: len(self._classes))
+    classes = property(lambda self: self._classes)
+    image_index = property(lambda self: list(range(len(self._paths))))
+    num_images = property(lambda self: len(self._paths))
+
+    def image_path_at(self, i):
+        return self._paths[i]
+
+    def competition_mode(self, on):
+        pass
+
+    def evaluate_detections(self, all_boxes, output_dir=None):
+        """No ground truth exists for these sets: writes a per-class detection count summary instead of AP."""
+        counts = [int(sum(len(d) for d in per_image)) for per_image in all_boxes]
+        if output_dir:
+            with open(os.path.join(output_dir, "detection_counts.pkl"), "wb") as f:
+                pickle.dump(counts, f)
+        print("detections per class:", counts[1:])
+        return counts
+
+
+def _synthetic(n, num_classes, h=375, w=500, seed=3):
+    import cv2
+    d = tempfile.mkdtemp(prefix="frcnn_synth_")
+    rng = np.random.default_rng(seed)
+    paths = []
+    for i in range(n):
+        im = cv2.blur(rng.integers(0, 256, (h, w, 3), dtype=np.uint8), (5, 5))
+        p = os.path.join(d, "%06d.png" % i)
+        cv2.imwrite(p, im)
+        paths.append(p)
+    return SimpleImdb("synthetic_%d_%d" % (n, num_classes), paths, num_classes)
+
+
+def get_imdb(name):
+    """'synthetic_<n>_<classes>' | 'dir:<path>:<classes>' | a name registered with register()."""
+    if name in _SETS:
+        return _SETS[name]()
+    if name.startswith("synthetic_"):
+        _, n, c = name.split("_")
+        return _synthetic(int(n), int(c))
+    if name.startswith("dir:"):
+        _, path, c = name.split(":")
+        files = sorted(os.path.join(path, f) for f in os.listdir(path) if f.lower().endswith((".jpg", ".jpeg", ".png")))
+        return SimpleImdb("dir_" + os.path.basename(os.path.normpath(path)), files, int(c))
+    raise KeyError('Unknown dataset: {}'.format(name))
+
+
+def register(name, fn):
+    _SETS[name] = fn
+
+
+def list_imdbs():
+    return list(_SETS.keys()) + ["synthetic_<n>_<classes>", "dir:<path>:<classes>"]

@@ -99,7 +99,8 @@ class Network(object):
             raise RuntimeError("no weights loaded: call load_weights() / Saver.restore() before test_image")
         key = (int(h), int(w))
         if key not in self._plans:
-            _native.check(_native.lib().frcnn_check_device(torch.cuda.current_device()), "check_device")
+            dev = torch.cuda.current_device() if torch.cuda.is_available() else 0
+            _native.check(_native.lib().frcnn_check_device(dev), "check_device")   # fails loudly: no CPU fallback exists
             self._plans[key] = engine.ShapePlan(self, key[0], key[1], use_graph=self.use_cuda_graph)
         return self._plans[key]
 

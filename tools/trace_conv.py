@@ -1,7 +1,7 @@
 """Debug aid (GPU box): dump the pipeline hand-off timeline of CTA(0,0) of one conv launch."""
 import sys, ctypes as C
 import numpy as np, torch
-sys.path.insert(0, ".")
+sys.path.insert(0, __import__("os").path.join(__import__("os").path.dirname(__import__("os").path.abspath(__file__)), ".."))
 from tf_faster_rcnn_b200 import ops, _native as N
 
 def trace(n, h, w, cin, cout, k, bn, kpc=2):
