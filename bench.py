@@ -99,11 +99,20 @@ def cpu_reference_step(key, weights, blob, im_info, C, scales, post):
     return sum(d.shape[0] for d in dets)
 
 
+def all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arm is entitled to every core the process may run on."""
+    import torch
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    torch.set_num_threads(max(1, n))
+    return torch.get_num_threads()
+
+
 def run_reference(args):
     import torch
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    all_host_threads()
     key, C, scales, H, W, post, label, weights, blob = make_inputs(args.net)
     im_info = np.array([H, W, 1.0], np.float32)
     cores = torch.get_num_threads()
@@ -250,6 +259,7 @@ def run_ours(args):
     }
     if not args.no_cpu_baseline and world == 1:
         import torch as _t
+        all_host_threads()
         t0 = time.perf_counter()
         cpu_reference_step(key, weights, blob, im_info, C, scales, post)      # warm-up (thread pools, oneDNN primitives)
         t1 = time.perf_counter()

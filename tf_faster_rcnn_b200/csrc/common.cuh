@@ -155,6 +155,19 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t* v)
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// read-only global loads the compiler may neither duplicate nor sink (asm volatile): used where the loads must be
+// issued early, all together, to hide their latency (conv epilogue)
+__device__ __forceinline__ float4 ld_nc_f4_pinned(const float* p) {
+  float4 v;
+  asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float ld_nc_f32_pinned(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+
 // round-to-nearest fp32 -> tf32 (result is an fp32 bit pattern with the low 13 mantissa bits clear)
 __device__ __forceinline__ float to_tf32(float x) {
   uint32_t r;

@@ -120,6 +120,7 @@ conv_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) FRCNN_TRACE2(700, 0);
 
   // tile coordinates
   const int mt = blockIdx.x;
@@ -147,6 +148,7 @@ conv_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) FRCNN_TRACE2(701, 0);
 
   if (warp == 8) {
     if (lane == 0) {
@@ -273,6 +275,7 @@ conv_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
 #pragma unroll
       for (int j = 0; j < 32; ++j) acc[c0 + j] = __fadd_rn(acc[c0 + j], __uint_as_float(v[j]));
     }
+    if (threadIdx.x == 128) FRCNN_TRACE2(702, 0);
     // ---------------- epilogue ----------------
     // r01 finding 4: writing each thread's own output row straight from registers (32 lanes = 32 rows, 8 KB apart) made
     // every global access 32 separate sectors and cost ~20 us per CTA.  The tile is therefore transposed through the
@@ -290,9 +293,10 @@ conv_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     const int dh = rem / p.tw, dw = rem % p.tw;
     const int n = n0 + dn, h = h0 + dh, w = w0 + dw;
     const bool valid = (row < p.tn * rows_img) && n < p.nimg && h < p.ho && w < p.wo;
-    const long long my_pix = valid ? (((long long)n * p.ho + h) * p.wo + w) : -1;
+    const int my_pix = valid ? (int)(((long long)n * p.ho + h) * p.wo + w) : -1;
     __syncwarp();
     constexpr int ROWS_PER_IT = 32 / CH;                    // 1 for BN=128, 2 for BN=64, 4 for BN=32
+    constexpr int ITERS = 32 / ROWS_PER_IT;
     const int cg = lane % CH;                               // column group of this lane
     const int rsub = lane / CH;
     const int c = nblk * BN + cg * 4;                       // first of this lane's 4 output channels
@@ -303,51 +307,82 @@ conv_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     const float* const scale = raw ? nullptr : p.scale;
     const float* const shift = raw ? nullptr : p.shift;
     const int act = raw ? FRCNN_ACT_NONE : p.act;
+    // r01 finding 5: with __ldg the compiler sank the scale/shift loads INTO the row loop (one ~400-cycle global load per
+    // row, 13k cycles per tile); all epilogue inputs are now loaded up front with pinned (asm volatile) loads.
     float sc[4] = {1.f, 1.f, 1.f, 1.f}, sh[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int e = 0; e < 4; ++e)
       if (c + e < p.cout) {
-        if (scale) sc[e] = __ldg(scale + c + e);
-        if (shift) sh[e] = __ldg(shift + c + e);
+        if (scale) sc[e] = ld_nc_f32_pinned(scale + c + e);
+        if (shift) sh[e] = ld_nc_f32_pinned(shift + c + e);
       }
-#pragma unroll 4
-    for (int it = 0; it < 32 / ROWS_PER_IT; ++it) {
-      const int r = it * ROWS_PER_IT + rsub;
-      const long long pix = __shfl_sync(0xffffffffu, my_pix, r);
-      if (pix < 0 || c >= p.cout) continue;
-      const float4 v = stage[r * CH + ((cg ^ r) & (CH - 1))];
-      float y[4] = {v.x, v.y, v.z, v.w};
-      float* optr = obase + (size_t)pix * p.cout + c;
-      float res[4] = {0.f, 0.f, 0.f, 0.f};
-      if (rbase) {
-        const float* rptr = rbase + (size_t)pix * p.cout + c;
-        if (vec_ok) { const float4 rv = __ldg(reinterpret_cast<const float4*>(rptr)); res[0] = rv.x; res[1] = rv.y; res[2] = rv.z; res[3] = rv.w; }
-        else {
+    int pixr[ITERS];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) if (c + e < p.cout) res[e] = __ldg(rptr + e);
+    for (int it = 0; it < ITERS; ++it) pixr[it] = __shfl_sync(0xffffffffu, my_pix, it * ROWS_PER_IT + rsub);
+    const bool col_ok = c < p.cout;
+    if (rbase && vec_ok) {
+      // residual tile in two batches: issue a batch of loads before their first use (accumulator registers are free now)
+      constexpr int HALF = ITERS > 16 ? 16 : ITERS;
+#pragma unroll
+      for (int base_it = 0; base_it < ITERS; base_it += HALF) {
+        float4 rv[HALF];
+#pragma unroll
+        for (int i = 0; i < HALF; ++i)
+          rv[i] = (pixr[base_it + i] >= 0 && col_ok) ? ld_nc_f4_pinned(rbase + (size_t)pixr[base_it + i] * p.cout + c)
+                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < HALF; ++i) {
+          const int it = base_it + i;
+          if (pixr[it] < 0 || !col_ok) continue;
+          const int r = it * ROWS_PER_IT + rsub;
+          const float4 v = stage[r * CH + ((cg ^ r) & (CH - 1))];
+          float y[4] = {v.x, v.y, v.z, v.w};
+          const float res[4] = {rv[i].x, rv[i].y, rv[i].z, rv[i].w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float a = y[e];
+            if (scale) a = __fmul_rn(a, sc[e]);
+            if (shift) a = __fadd_rn(a, sh[e]);
+            a = __fadd_rn(a, res[e]);
+            if (act == FRCNN_ACT_RELU) a = fmaxf(a, 0.f);
+            else if (act == FRCNN_ACT_RELU6) a = fminf(fmaxf(a, 0.f), 6.f);
+            y[e] = a;
+          }
+          *reinterpret_cast<float4*>(obase + (size_t)pixr[it] * p.cout + c) = make_float4(y[0], y[1], y[2], y[3]);
         }
       }
+    } else {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        float a = y[e];
-        if (scale) a = __fmul_rn(a, sc[e]);
-        if (shift) a = __fadd_rn(a, sh[e]);
-        if (rbase) a = __fadd_rn(a, res[e]);
-        if (act == FRCNN_ACT_RELU) a = fmaxf(a, 0.f);
-        else if (act == FRCNN_ACT_RELU6) a = fminf(fmaxf(a, 0.f), 6.f);
-        y[e] = a;
-      }
-      if (vec_ok) {
-        *reinterpret_cast<float4*>(optr) = make_float4(y[0], y[1], y[2], y[3]);
-      } else {
+      for (int it = 0; it < ITERS; ++it) {
+        if (pixr[it] < 0 || !col_ok) continue;
+        const int r = it * ROWS_PER_IT + rsub;
+        const float4 v = stage[r * CH + ((cg ^ r) & (CH - 1))];
+        float y[4] = {v.x, v.y, v.z, v.w};
+        float* optr = obase + (size_t)pixr[it] * p.cout + c;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) if (c + e < p.cout) optr[e] = y[e];
+        for (int e = 0; e < 4; ++e) {
+          float a = y[e];
+          if (scale) a = __fmul_rn(a, sc[e]);
+          if (shift) a = __fadd_rn(a, sh[e]);
+          if (rbase && c + e < p.cout) a = __fadd_rn(a, __ldg(rbase + (size_t)pixr[it] * p.cout + c + e));
+          if (act == FRCNN_ACT_RELU) a = fmaxf(a, 0.f);
+          else if (act == FRCNN_ACT_RELU6) a = fminf(fmaxf(a, 0.f), 6.f);
+          y[e] = a;
+        }
+        if (vec_ok) {
+          *reinterpret_cast<float4*>(optr) = make_float4(y[0], y[1], y[2], y[3]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) if (c + e < p.cout) optr[e] = y[e];
+        }
       }
     }
   }
+  if (threadIdx.x == 128) FRCNN_TRACE2(703, 0);
   tc_fence_before();
   __syncthreads();
   if (warp == 8) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
+  if (threadIdx.x == 256) FRCNN_TRACE2(704, 0);
 }
 
 // split-K second pass: out = act((sum_z ws[z]) * scale + shift (+ residual)), z summed in index order (deterministic)
