@@ -162,6 +162,34 @@ def run_ours(args):
         net.use_cuda_graph = False
     plan = net.plan_for(H, W)
     plan.image.copy_(host_blob)
+    if args.layers:
+        net.use_cuda_graph = False
+        for _ in range(3):
+            plan.tape.run()
+        torch.cuda.synchronize()
+        rows = []
+        for lbl, fn in plan.tape.steps:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            rows.append((lbl, e0.elapsed_time(e1) * 1000 / 5))
+        tot = sum(t for _, t in rows)
+        print("per-launch times (us, warm, back-to-back x5), total %.0f us over %d steps" % (tot, len(rows)))
+        groups = {}
+        for lbl, t in rows:
+            kind = lbl.split(":")[0]
+            key = kind
+            if kind == "conv":
+                key = "conv:" + ("head" if "/block4/" in lbl or "cls_bbox" in lbl or "/fc" in lbl else "rpn" if "/rpn" in lbl else "body")
+            groups[key] = groups.get(key, 0) + t
+        for k, v in sorted(groups.items(), key=lambda kv: -kv[1]):
+            print("  %-16s %8.0f us  %5.1f%%" % (k, v, 100 * v / tot))
+        for lbl, t in rows:
+            print("    %-70s %8.1f" % (lbl, t))
+        return
     if args.ncu:
         plan.launch(1.0, H, W, post=True, detect=True)
         torch.cuda.synchronize()
@@ -283,6 +311,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--net", default="res101", choices=sorted(NETS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--layers", action="store_true", help="print a per-launch CUDA-event timing table of one image (eager, warm) and exit")
     ap.add_argument("--ncu", action="store_true", help="profiling aid: eager launches (no CUDA graph), one warm-up image, then ONE image "
                     "between cudaProfilerStart/Stop (run under `ncu --profile-from-start off`); prints no bench line")
     args = ap.parse_args()

@@ -90,7 +90,7 @@ typedef struct {
   int pad_t, pad_l;          /* zero padding before the first row / column */
   int ho, wo;
   int act;                   /* FRCNN_ACT_* */
-  int block_n;               /* 0 = choose; else 32/64/128 */
+  int block_n;               /* 0 = choose; else 64/128 */
   int kb_per_chunk;          /* 0 = default (8): 32-wide k-blocks summed in TMEM before promotion to registers */
   int split_k;               /* 0 = choose; 1 = never; n = split the K loop over n CTAs + deterministic reduce pass */
 } frcnn_conv_desc;

@@ -53,7 +53,6 @@ def run_conv(x, w, stride, mode, scale=None, shift=None, residual=None, act=0, b
 CASES = [
     # name, n, h, w, cin, cout, k, stride, mode, block_n
     ("fc_small", 1, 1, 300, 64, 64, 1, 1, "SAME", 0),
-    ("pw_1900_bn32", 1, 38, 50, 256, 256, 1, 1, "SAME", 32),
     ("pw_1900_bn64", 1, 38, 50, 256, 256, 1, 1, "SAME", 64),
     ("pw_1900_bn128", 1, 38, 50, 1024, 256, 1, 1, "SAME", 128),
     ("c3_s1_64", 1, 38, 50, 64, 64, 3, 1, "SAME", 0),

@@ -26,14 +26,14 @@
 // 1/2/4/8 k-blocks -> 6e-7/7e-7/1.0e-6/1.9e-6 error vs fp64, the fp32 CPU reference sitting at 0.6e-6..2e-6).  Hence
 // the D_main / D_small separation described at the TMEM map below, and a default chunk of 8 k-blocks.
 //
-// Warp roles (320 threads, 1 CTA/SM), rings are 4 deep (index kb & 3).  The MMA issuer is the HIGHEST warp id of its
-// scheduler partition on purpose: the arbiter favours high warp ids, and with the issuer at warp 1 the epilogue's
-// burst of tcgen05.ld + FADDs delayed every chunk hand-over by ~900 cycles (profiles/r01 trace).
-//   warp 8      TMA producer      A: wait a_empty[s] -> a_full[s];  B: wait mma_done[s] -> full[s] (tx)
+// PERSISTENT: grid = #SMs; every role walks the same sequence of work units (output tile x split-K range); ring slots and
+// barrier phases run on across units, so the next unit's loads / splits / MMAs overlap this unit's epilogue stores.
+// Warp roles (448 threads, 1 CTA/SM), rings are 4 deep (index kb & 3):
+//   warp 12     TMA producer      A: wait a_empty[s] -> a_full[s];  B: wait mma_done[s] -> full[s] (tx)
 //   warps 0..3  operand splitter  wait a_full[s], mma_done[s]; smem row -> hi/lo -> tcgen05.st; arrive a_empty[s], full[s]
-//   warp 9      MMA issuer        wait full[s] (B landed + A stored); 4 k-slices x 3 tcgen05.mma (TS); commit -> mma_done[s];
+//   warp 13     MMA issuer        wait full[s] (B landed + A stored); 4 k-slices x 3 tcgen05.mma (TS); commit -> mma_done[s];
 //                                 per chunk: wait acc_empty first, commit -> acc_full last
-//   warps 4..7  accumulate+epilogue  per chunk: wait acc_full; tcgen05.ld D_main; acc += partial; arrive acc_empty;
+//   warps 4..11 accumulate+epilogue (two per TMEM lane quarter, half the columns each)  per chunk: wait acc_full; tcgen05.ld D_main; acc += partial; arrive acc_empty;
 //                                 finally y = act(acc*scale + shift (+res)); st.global
 // TMEM map (512 columns): [0, BN) D_main = chunk partial of the a_hi*b_hi products; [128, 128+BN) D_small = the two
 // cross terms a_lo*b_hi + a_hi*b_lo over the WHOLE k loop (2^-11 of the result, so its truncation is harmless and it is
@@ -49,9 +49,9 @@ namespace frcnn {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 32;                          // fp32 elements: 128 B = one swizzle row
 constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 4;  // 16 KiB
-constexpr int NUM_THREADS = 320;
+constexpr int NUM_THREADS = 448;
 constexpr int SPLIT_THREADS = 128;
-constexpr int EPI_THREADS = 128;
+constexpr int EPI_THREADS = 256;                     // 8 warps: two per TMEM lane quarter, each owning half the columns
 constexpr int RING = 4;                              // depth of the A-raw, B and TMEM-A rings
 constexpr int TMEM_COLS = 512;
 constexpr int TMEM_A_COL0 = 256;
@@ -68,7 +68,8 @@ struct ConvKernelParams {
   int act;
   int a_box_bytes;
   int kb_per_chunk;   // k-blocks accumulated in TMEM before promotion to registers
-  int kb_per_split;   // split-K: blockIdx.z handles k-blocks [z*kb_per_split, ...); == total when not split
+  int kb_per_split;   // split-K: split z handles k-blocks [z*kb_per_split, ...); == total when not split
+  int m_tiles, n_tiles, total_units;   // persistent loop: unit u = mt + m_tiles*(nblk + n_tiles*z)
   float* ws;          // split-K workspace [splits][out elements] (raw partial sums) or NULL
   long long out_elems;
   long long* trace;   // debug: clock64() stamps of CTA (0,0)'s pipeline hand-offs; normally NULL
@@ -83,8 +84,11 @@ struct ConvKernelParams {
     if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && (kbv) < 64) p.trace[(kbv) * 8 + (slot)] = clock64(); \
   } while (0)
 
+constexpr int STAGE_BYTES = 8 * 32 * 32 * 4;          // epilogue transposition buffer: 8 warps x 32 rows x 32 columns fp32
 template <int BN> constexpr int b_stage_bytes() { return 2 * BN * BLOCK_K * 4; }
-template <int BN> constexpr int smem_bytes() { return RING * (A_TILE_BYTES + b_stage_bytes<BN>()) + 1024 /*align slack*/ + 256 /*barriers*/; }
+template <int BN> constexpr int smem_bytes() {
+  return RING * (A_TILE_BYTES + b_stage_bytes<BN>()) + STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+}
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (8-row x 128 B atoms, 1024 B apart)
 __device__ __forceinline__ uint64_t sw128_desc(uint32_t saddr) {
@@ -95,6 +99,25 @@ __device__ __forceinline__ uint64_t sw128_desc(uint32_t saddr) {
   d |= (uint64_t)1 << 46;                  // descriptor version (sm_100)
   d |= (uint64_t)2 << 61;                  // SWIZZLE_128B
   return d;
+}
+
+// Work unit u (persistent loop: u = blockIdx.x, += gridDim.x) -> output tile + split-K range.
+struct Unit {
+  int w0, h0, n0, nblk, z, kb0, num_kb;
+};
+__device__ __forceinline__ Unit decode_unit(const ConvKernelParams& p, int u, int num_kb_total) {
+  Unit t;
+  const int mt = u % p.m_tiles;
+  const int rest = u / p.m_tiles;
+  t.nblk = rest % p.n_tiles;
+  t.z = rest / p.n_tiles;
+  const int tile_w = mt % p.tiles_w;
+  const int tile_h = (mt / p.tiles_w) % p.tiles_h;
+  const int tile_n = mt / (p.tiles_w * p.tiles_h);
+  t.w0 = tile_w * p.tw; t.h0 = tile_h * p.th; t.n0 = tile_n * p.tn;
+  t.kb0 = t.z * p.kb_per_split;
+  t.num_kb = min(p.kb_per_split, num_kb_total - t.kb0);
+  return t;
 }
 
 template <int BN>
@@ -110,7 +133,8 @@ conv_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;                               // RING x 16 KiB raw fp32 A tiles (TMA, swizzled)
   uint8_t* smem_b = smem + RING * A_TILE_BYTES;         // RING x (B_hi | B_lo)
-  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem_b + RING * kBStage);
+  uint8_t* smem_stage = smem_b + RING * kBStage;        // epilogue transposition buffer (own region: overlaps next tile's loads)
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem_stage + STAGE_BYTES);
   uint64_t* a_empty = a_full + RING;
   uint64_t* full = a_empty + RING;            // B bytes landed (tx) AND the 128 splitter threads stored A hi/lo
   uint64_t* mma_done = full + RING;
@@ -121,20 +145,9 @@ conv_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   if (threadIdx.x == 0) FRCNN_TRACE2(700, 0);
-
-  // tile coordinates
-  const int mt = blockIdx.x;
-  const int tile_w = mt % p.tiles_w;
-  const int tile_h = (mt / p.tiles_w) % p.tiles_h;
-  const int tile_n = mt / (p.tiles_w * p.tiles_h);
-  const int w0 = tile_w * p.tw, h0 = tile_h * p.th, n0 = tile_n * p.tn;
-  const int nblk = blockIdx.y;
   const int num_kb_total = p.kh * p.kw * (p.cin / BLOCK_K);
-  const int kb0 = blockIdx.z * p.kb_per_split;                  // split-K range of this CTA
-  const int num_kb = min(p.kb_per_split, num_kb_total - kb0);
-  const int num_chunks = (num_kb + p.kb_per_chunk - 1) / p.kb_per_chunk;
 
-  if (warp == 8 && lane == 0) {
+  if (warp == 12 && lane == 0) {
     tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmBhi); tma_prefetch_desc(&tmBlo);
     for (int s = 0; s < RING; ++s) {
       mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], SPLIT_THREADS);
@@ -143,71 +156,79 @@ conv_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     mbar_init(acc_full, 1); mbar_init(acc_empty, EPI_THREADS);
     mbar_fence_init();
   }
-  if (warp == 8) { tmem_alloc(tmem_slot, TMEM_COLS); tmem_relinquish(); }
+  if (warp == 12) { tmem_alloc(tmem_slot, TMEM_COLS); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (threadIdx.x == 0) FRCNN_TRACE2(701, 0);
 
-  if (warp == 8) {
+  // Every role walks the same unit sequence; ring slots / barrier phases run on across units (kbt, ct are running totals).
+  if (warp == 12) {
     if (lane == 0) {
       const int cchunks = p.cin / BLOCK_K;
+      int kbt = 0;
+      for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
+        const Unit t = decode_unit(p, u, num_kb_total);
 #pragma unroll 1
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int g = kb0 + kb;                                 // global k-block -> (filter tap, channel chunk)
-        const int tap = g / cchunks, kc = g - tap * cchunks;
-        const int r = tap / p.kw, s = tap - r * p.kw;
-        const int slot = kb & (RING - 1);
-        const uint32_t par = (uint32_t)(kb / RING) & 1u;
-        mbar_wait(&a_empty[slot], par ^ 1u);                 // splitter has consumed the raw tile
-        mbar_expect_tx(&a_full[slot], (uint32_t)p.a_box_bytes);
-        tma_load_4d(smem_a + slot * A_TILE_BYTES, &tmA, &a_full[slot], kc * BLOCK_K, w0 * p.stride + s - p.pad_l,
-                    h0 * p.stride + r - p.pad_t, n0);
-        mbar_wait(&mma_done[slot], par ^ 1u);                // MMAs that read this B slot have completed
-        FRCNN_TRACE(0, kb);
-        mbar_expect_tx(&full[slot], (uint32_t)(2 * kBTile));
-        const int kcoord = tap * p.cin + kc * BLOCK_K;
-        tma_load_2d(smem_b + slot * kBStage, &tmBhi, &full[slot], kcoord, nblk * BN);
-        tma_load_2d(smem_b + slot * kBStage + kBTile, &tmBlo, &full[slot], kcoord, nblk * BN);
-        FRCNN_TRACE(1, kb);
+        for (int kb = 0; kb < t.num_kb; ++kb, ++kbt) {
+          const int g = t.kb0 + kb;                               // global k-block -> (filter tap, channel chunk)
+          const int tap = g / cchunks, kc = g - tap * cchunks;
+          const int r = tap / p.kw, s = tap - r * p.kw;
+          const int slot = kbt & (RING - 1);
+          const uint32_t par = (uint32_t)(kbt / RING) & 1u;
+          mbar_wait(&a_empty[slot], par ^ 1u);                 // splitter has consumed the raw tile
+          mbar_expect_tx(&a_full[slot], (uint32_t)p.a_box_bytes);
+          tma_load_4d(smem_a + slot * A_TILE_BYTES, &tmA, &a_full[slot], kc * BLOCK_K, t.w0 * p.stride + s - p.pad_l,
+                      t.h0 * p.stride + r - p.pad_t, t.n0);
+          mbar_wait(&mma_done[slot], par ^ 1u);                // MMAs that read this B slot have completed
+          FRCNN_TRACE(0, kbt);
+          mbar_expect_tx(&full[slot], (uint32_t)(2 * kBTile));
+          const int kcoord = tap * p.cin + kc * BLOCK_K;
+          tma_load_2d(smem_b + slot * kBStage, &tmBhi, &full[slot], kcoord, t.nblk * BN);
+          tma_load_2d(smem_b + slot * kBStage + kBTile, &tmBlo, &full[slot], kcoord, t.nblk * BN);
+          FRCNN_TRACE(1, kbt);
+        }
       }
     }
     __syncwarp();
-  } else if (warp == 9) {
+  } else if (warp == 13) {
     if (lane == 0) {
-      // one flat loop (chunk bookkeeping inline) so that the chunk hand-over runs the same, hot, instruction lines
-      int in_chunk = 0, c = 0;
+      int kbt = 0, ct = 0;
       const uint32_t d_main = tmem_base, d_small = tmem_base + 128u;
+      for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
+        const Unit t = decode_unit(p, u, num_kb_total);
+        int in_chunk = 0;
 #pragma unroll 1
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int slot = kb & (RING - 1);
-        const uint32_t par = (uint32_t)(kb / RING) & 1u;
-        if (in_chunk == 0) {
-          mbar_wait(acc_empty, ((uint32_t)c & 1u) ^ 1u);           // previous chunk partial has been promoted
-          FRCNN_TRACE2(576, c);
-        }
-        mbar_wait(&full[slot], par);
-        tc_fence_after();
-        FRCNN_TRACE(4, kb);
-        const uint32_t sb = smem_u32(smem_b + slot * kBStage);
-        const uint64_t b_hi = sw128_desc(sb);
-        const uint64_t b_lo = sw128_desc(sb + kBTile);
-        const uint32_t a_hi = tmem_base + (uint32_t)(TMEM_A_COL0 + slot * 64);
-        const uint32_t a_lo = a_hi + 32u;
+        for (int kb = 0; kb < t.num_kb; ++kb, ++kbt) {
+          const int slot = kbt & (RING - 1);
+          const uint32_t par = (uint32_t)(kbt / RING) & 1u;
+          if (in_chunk == 0) {
+            mbar_wait(acc_empty, ((uint32_t)ct & 1u) ^ 1u);          // previous chunk partial (and, across units, D_small) has been read
+            FRCNN_TRACE2(576, ct);
+          }
+          mbar_wait(&full[slot], par);
+          tc_fence_after();
+          FRCNN_TRACE(4, kbt);
+          const uint32_t sb = smem_u32(smem_b + slot * kBStage);
+          const uint64_t b_hi = sw128_desc(sb);
+          const uint64_t b_lo = sw128_desc(sb + kBTile);
+          const uint32_t a_hi = tmem_base + (uint32_t)(TMEM_A_COL0 + slot * 64);
+          const uint32_t a_lo = a_hi + 32u;
 #pragma unroll
-        for (int k = 0; k < BLOCK_K / 8; ++k) {
-          const uint64_t off = (uint64_t)(k * 8 * 4) >> 4;   // B: advance 8 tf32 = 32 B inside the swizzle row
-          const uint32_t ak = (uint32_t)(k * 8);             // A: 8 tf32 = 8 TMEM columns
-          umma_tf32_ts(d_small, a_lo + ak, b_hi + off, kIdesc, (k > 0 || kb > 0) ? 1u : 0u);
-          umma_tf32_ts(d_small, a_hi + ak, b_lo + off, kIdesc, 1u);
-          umma_tf32_ts(d_main, a_hi + ak, b_hi + off, kIdesc, (k > 0 || in_chunk > 0) ? 1u : 0u);
-        }
-        umma_commit(&mma_done[slot]);
-        FRCNN_TRACE(5, kb);
-        if (++in_chunk == p.kb_per_chunk || kb + 1 == num_kb) {
-          umma_commit(acc_full);
-          in_chunk = 0; ++c;
+          for (int k = 0; k < BLOCK_K / 8; ++k) {
+            const uint64_t off = (uint64_t)(k * 8 * 4) >> 4;   // B: advance 8 tf32 = 32 B inside the swizzle row
+            const uint32_t ak = (uint32_t)(k * 8);             // A: 8 tf32 = 8 TMEM columns
+            umma_tf32_ts(d_small, a_lo + ak, b_hi + off, kIdesc, (k > 0 || kb > 0) ? 1u : 0u);
+            umma_tf32_ts(d_small, a_hi + ak, b_lo + off, kIdesc, 1u);
+            umma_tf32_ts(d_main, a_hi + ak, b_hi + off, kIdesc, (k > 0 || in_chunk > 0) ? 1u : 0u);
+          }
+          umma_commit(&mma_done[slot]);
+          FRCNN_TRACE(5, kbt);
+          if (++in_chunk == p.kb_per_chunk || kb + 1 == t.num_kb) {
+            umma_commit(acc_full);
+            in_chunk = 0; ++ct;
+          }
         }
       }
     }
@@ -217,172 +238,168 @@ conv_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const uint32_t lane_field = (uint32_t)(q * 32) << 16;
-    for (int kb = 0; kb < num_kb; ++kb) {
-      const int slot = kb & (RING - 1);
-      const uint32_t par = (uint32_t)(kb / RING) & 1u;
-      mbar_wait(&a_full[slot], par);
-      // SWIZZLE_128B: 16-byte chunk c of row r sits at chunk (c ^ (r & 7)); quarter-warp phases are conflict-free
-      const uint8_t* arow = smem_a + slot * A_TILE_BYTES + row * 128;
-      uint32_t hi[32], lo[32];
+    int kbt = 0;
+    for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
+      const Unit t = decode_unit(p, u, num_kb_total);
+#pragma unroll 1
+      for (int kb = 0; kb < t.num_kb; ++kb, ++kbt) {
+        const int slot = kbt & (RING - 1);
+        const uint32_t par = (uint32_t)(kbt / RING) & 1u;
+        mbar_wait(&a_full[slot], par);
+        // SWIZZLE_128B: 16-byte chunk c of row r sits at chunk (c ^ (r & 7)); quarter-warp phases are conflict-free
+        const uint8_t* arow = smem_a + slot * A_TILE_BYTES + row * 128;
+        uint32_t hi[32], lo[32];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const float4 v = *reinterpret_cast<const float4*>(arow + ((c ^ (row & 7)) << 4));
-        const float h0 = to_tf32(v.x), h1 = to_tf32(v.y), h2 = to_tf32(v.z), h3 = to_tf32(v.w);
-        hi[4 * c + 0] = __float_as_uint(h0); hi[4 * c + 1] = __float_as_uint(h1);
-        hi[4 * c + 2] = __float_as_uint(h2); hi[4 * c + 3] = __float_as_uint(h3);
-        lo[4 * c + 0] = __float_as_uint(to_tf32(__fsub_rn(v.x, h0))); lo[4 * c + 1] = __float_as_uint(to_tf32(__fsub_rn(v.y, h1)));
-        lo[4 * c + 2] = __float_as_uint(to_tf32(__fsub_rn(v.z, h2))); lo[4 * c + 3] = __float_as_uint(to_tf32(__fsub_rn(v.w, h3)));
+        for (int c = 0; c < 8; ++c) {
+          const float4 v = *reinterpret_cast<const float4*>(arow + ((c ^ (row & 7)) << 4));
+          const float h0 = to_tf32(v.x), h1 = to_tf32(v.y), h2 = to_tf32(v.z), h3 = to_tf32(v.w);
+          hi[4 * c + 0] = __float_as_uint(h0); hi[4 * c + 1] = __float_as_uint(h1);
+          hi[4 * c + 2] = __float_as_uint(h2); hi[4 * c + 3] = __float_as_uint(h3);
+          lo[4 * c + 0] = __float_as_uint(to_tf32(__fsub_rn(v.x, h0))); lo[4 * c + 1] = __float_as_uint(to_tf32(__fsub_rn(v.y, h1)));
+          lo[4 * c + 2] = __float_as_uint(to_tf32(__fsub_rn(v.z, h2))); lo[4 * c + 3] = __float_as_uint(to_tf32(__fsub_rn(v.w, h3)));
+        }
+        mbar_arrive(&a_empty[slot]);                          // raw tile consumed (values are in registers)
+        mbar_wait(&mma_done[slot], par ^ 1u);                  // TMEM A slot no longer read by the tensor core
+        tc_fence_after();
+        const uint32_t ta = tmem_base + lane_field + (uint32_t)(TMEM_A_COL0 + slot * 64);
+        tmem_st_32x32(ta, hi);
+        tmem_st_32x32(ta + 32u, lo);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&full[slot]);
+        if (threadIdx.x == 0) FRCNN_TRACE(3, kbt);
       }
-      mbar_arrive(&a_empty[slot]);                          // raw tile consumed (values are in registers)
-      mbar_wait(&mma_done[slot], par ^ 1u);                  // TMEM A slot no longer read by the tensor core
-      tc_fence_after();
-      const uint32_t ta = tmem_base + lane_field + (uint32_t)(TMEM_A_COL0 + slot * 64);
-      tmem_st_32x32(ta, hi);
-      tmem_st_32x32(ta + 32u, lo);
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(&full[slot]);
-      if (threadIdx.x == 0) FRCNN_TRACE(3, kb);
     }
   } else {
-    // ---------------- accumulate (TMEM chunk partials -> fp32 registers, RN adds) ----------------
-    const int q = warp & 3;                 // TMEM lane quarter this warp may access
-    float acc[BN];
+    // ---------------- accumulate (TMEM chunk partials -> fp32 registers, RN adds) + epilogue ----------------
+    constexpr int W = BN / 2;                 // columns owned by this warp (two warps share a TMEM lane quarter)
+    const int q = warp & 3;                   // TMEM lane quarter this warp may access
+    const int col0 = ((warp - 4) >> 2) * W;
+    const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col0;
+    int ct = 0;
+    for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
+      const Unit t = decode_unit(p, u, num_kb_total);
+      const int num_chunks = (t.num_kb + p.kb_per_chunk - 1) / p.kb_per_chunk;
+      float acc[W];
 #pragma unroll
-    for (int j = 0; j < BN; ++j) acc[j] = 0.f;
-    for (int c = 0; c < num_chunks; ++c) {
-      mbar_wait(acc_full, (uint32_t)c & 1u);
-      tc_fence_after();
-      if (threadIdx.x == 128) FRCNN_TRACE(7, c);
+      for (int j = 0; j < W; ++j) acc[j] = 0.f;
+      for (int c = 0; c < num_chunks; ++c, ++ct) {
+        mbar_wait(acc_full, (uint32_t)ct & 1u);
+        tc_fence_after();
+        if (threadIdx.x == 128) FRCNN_TRACE(7, ct);
 #pragma unroll
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-        tmem_ld_wait();
+        for (int c0 = 0; c0 < W; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(tq + (uint32_t)c0, v);
+          tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) acc[c0 + j] = __fadd_rn(acc[c0 + j], __uint_as_float(v[j]));
+          for (int j = 0; j < 32; ++j) acc[c0 + j] = __fadd_rn(acc[c0 + j], __uint_as_float(v[j]));
+        }
+        if (c + 1 == num_chunks) {
+          // the cross terms of the unit's whole k range (complete: this acc_full commit covered every MMA)
+#pragma unroll
+          for (int c0 = 0; c0 < W; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld_32x32(tq + (uint32_t)(128 + c0), v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[c0 + j] = __fadd_rn(acc[c0 + j], __uint_as_float(v[j]));
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(acc_empty);               // the MMA warp may overwrite D_main (and, for the next unit, D_small)
+        if (threadIdx.x == 128) FRCNN_TRACE2(512, ct);
       }
-      tc_fence_before();
-      mbar_arrive(acc_empty);
-      if (threadIdx.x == 128) FRCNN_TRACE2(512, c);
-    }
-    // the cross terms of the whole k loop (complete: the last acc_full commit covered every MMA)
+      if (threadIdx.x == 128) FRCNN_TRACE2(702, 0);
+      // ---------------- epilogue (overlaps the next unit's main loop) ----------------
+      // r01 finding 4: writing each thread's own output row straight from registers (32 lanes = 32 rows, 8 KB apart) made
+      // every global access 32 separate sectors.  The tile is transposed through shared memory 32 columns at a time: thread =
+      // row writes XOR-swizzled 16-byte chunks (conflict free), then each lane owns 4 fixed channels and walks the warp's rows
+      // with coalesced 128-bit accesses (one full 128-byte line per row).  r01 finding 5: epilogue inputs are loaded with
+      // pinned (asm volatile) loads -- with __ldg the compiler sank the scale/shift loads into the row loop.
+      constexpr int CH = 8;                                   // 16-byte chunks per staged 32-column row
+      constexpr int ROWS_PER_IT = 4;
+      constexpr int ITERS = 8;
+      float4* stage = reinterpret_cast<float4*>(smem_stage + (warp - 4) * (32 * 32 * 4));
+      const int row = q * 32 + lane;
+      const int rows_img = p.th * p.tw;
+      const int dn = row / rows_img, rem = row % rows_img;
+      const int dh = rem / p.tw, dw = rem % p.tw;
+      const int n = t.n0 + dn, h = t.h0 + dh, w = t.w0 + dw;
+      const bool valid = (row < p.tn * rows_img) && n < p.nimg && h < p.ho && w < p.wo;
+      const int my_pix = valid ? (int)(((long long)n * p.ho + h) * p.wo + w) : -1;
+      const int cg = lane & (CH - 1);                         // column group of this lane
+      const int rsub = lane >> 3;
+      const bool vec_ok = (p.cout & 3) == 0;
+      const bool raw = p.ws != nullptr;                       // split-K: plain partial sums, epilogue runs in the reduce kernel
+      float* const obase = raw ? p.ws + (size_t)t.z * p.out_elems : p.out;
+      const float* const rbase = raw ? nullptr : p.residual;
+      const float* const scale = raw ? nullptr : p.scale;
+      const float* const shift = raw ? nullptr : p.shift;
+      const int act = raw ? FRCNN_ACT_NONE : p.act;
+      int pixr[ITERS];
 #pragma unroll
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t v[32];
-      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(128 + c0), v);
-      tmem_ld_wait();
+      for (int it = 0; it < ITERS; ++it) pixr[it] = __shfl_sync(0xffffffffu, my_pix, it * ROWS_PER_IT + rsub);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) acc[c0 + j] = __fadd_rn(acc[c0 + j], __uint_as_float(v[j]));
-    }
-    if (threadIdx.x == 128) FRCNN_TRACE2(702, 0);
-    // ---------------- epilogue ----------------
-    // r01 finding 4: writing each thread's own output row straight from registers (32 lanes = 32 rows, 8 KB apart) made
-    // every global access 32 separate sectors and cost ~20 us per CTA.  The tile is therefore transposed through the
-    // (now idle) A-raw ring: thread = row writes its BN values as XOR-swizzled 16-byte chunks (conflict free), then
-    // each lane owns 4 fixed output channels and walks the warp's 32 rows with fully coalesced 128-bit accesses.
-    constexpr int CH = BN / 4;                              // 16-byte chunks per row
-    float4* stage = reinterpret_cast<float4*>(smem_a + q * (32 * BN * 4));
+      for (int pass = 0; pass < W / 32; ++pass) {
+        const int c = t.nblk * BN + col0 + pass * 32 + cg * 4;   // first of this lane's 4 output channels in this pass
+        const bool col_ok = c < p.cout;
+        float sc[4] = {1.f, 1.f, 1.f, 1.f}, sh[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int j = 0; j < CH; ++j)
-      stage[lane * CH + ((j ^ lane) & (CH - 1))] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
-    // pixel offset of this thread's row (shuffled to the lanes that write it)
-    const int row = q * 32 + lane;
-    const int rows_img = p.th * p.tw;
-    const int dn = row / rows_img, rem = row % rows_img;
-    const int dh = rem / p.tw, dw = rem % p.tw;
-    const int n = n0 + dn, h = h0 + dh, w = w0 + dw;
-    const bool valid = (row < p.tn * rows_img) && n < p.nimg && h < p.ho && w < p.wo;
-    const int my_pix = valid ? (int)(((long long)n * p.ho + h) * p.wo + w) : -1;
-    __syncwarp();
-    constexpr int ROWS_PER_IT = 32 / CH;                    // 1 for BN=128, 2 for BN=64, 4 for BN=32
-    constexpr int ITERS = 32 / ROWS_PER_IT;
-    const int cg = lane % CH;                               // column group of this lane
-    const int rsub = lane / CH;
-    const int c = nblk * BN + cg * 4;                       // first of this lane's 4 output channels
-    const bool vec_ok = (p.cout & 3) == 0;
-    const bool raw = p.ws != nullptr;                       // split-K: plain partial sums, epilogue runs in the reduce kernel
-    float* const obase = raw ? p.ws + (size_t)blockIdx.z * p.out_elems : p.out;
-    const float* const rbase = raw ? nullptr : p.residual;
-    const float* const scale = raw ? nullptr : p.scale;
-    const float* const shift = raw ? nullptr : p.shift;
-    const int act = raw ? FRCNN_ACT_NONE : p.act;
-    // r01 finding 5: with __ldg the compiler sank the scale/shift loads INTO the row loop (one ~400-cycle global load per
-    // row, 13k cycles per tile); all epilogue inputs are now loaded up front with pinned (asm volatile) loads.
-    float sc[4] = {1.f, 1.f, 1.f, 1.f}, sh[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int e = 0; e < 4; ++e)
+          if (c + e < p.cout) {
+            if (scale) sc[e] = ld_nc_f32_pinned(scale + c + e);
+            if (shift) sh[e] = ld_nc_f32_pinned(shift + c + e);
+          }
+        float4 rv[ITERS];
+        const bool res_vec = rbase && vec_ok;
+        if (res_vec) {
 #pragma unroll
-    for (int e = 0; e < 4; ++e)
-      if (c + e < p.cout) {
-        if (scale) sc[e] = ld_nc_f32_pinned(scale + c + e);
-        if (shift) sh[e] = ld_nc_f32_pinned(shift + c + e);
-      }
-    int pixr[ITERS];
+          for (int it = 0; it < ITERS; ++it)
+            rv[it] = (pixr[it] >= 0 && col_ok) ? ld_nc_f4_pinned(rbase + (size_t)pixr[it] * p.cout + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        __syncwarp();                                           // previous pass's reads are done
 #pragma unroll
-    for (int it = 0; it < ITERS; ++it) pixr[it] = __shfl_sync(0xffffffffu, my_pix, it * ROWS_PER_IT + rsub);
-    const bool col_ok = c < p.cout;
-    if (rbase && vec_ok) {
-      // residual tile in two batches: issue a batch of loads before their first use (accumulator registers are free now)
-      constexpr int HALF = ITERS > 16 ? 16 : ITERS;
+        for (int j = 0; j < CH; ++j) {
+          const int a0 = pass * 32 + 4 * j;
+          stage[lane * CH + ((j ^ lane) & (CH - 1))] = make_float4(acc[a0], acc[a0 + 1], acc[a0 + 2], acc[a0 + 3]);
+        }
+        __syncwarp();
 #pragma unroll
-      for (int base_it = 0; base_it < ITERS; base_it += HALF) {
-        float4 rv[HALF];
-#pragma unroll
-        for (int i = 0; i < HALF; ++i)
-          rv[i] = (pixr[base_it + i] >= 0 && col_ok) ? ld_nc_f4_pinned(rbase + (size_t)pixr[base_it + i] * p.cout + c)
-                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int i = 0; i < HALF; ++i) {
-          const int it = base_it + i;
+        for (int it = 0; it < ITERS; ++it) {
           if (pixr[it] < 0 || !col_ok) continue;
           const int r = it * ROWS_PER_IT + rsub;
           const float4 v = stage[r * CH + ((cg ^ r) & (CH - 1))];
           float y[4] = {v.x, v.y, v.z, v.w};
-          const float res[4] = {rv[i].x, rv[i].y, rv[i].z, rv[i].w};
+          float res[4] = {0.f, 0.f, 0.f, 0.f};
+          if (res_vec) { res[0] = rv[it].x; res[1] = rv[it].y; res[2] = rv[it].z; res[3] = rv[it].w; }
+          float* optr = obase + (size_t)pixr[it] * p.cout + c;
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             float a = y[e];
             if (scale) a = __fmul_rn(a, sc[e]);
             if (shift) a = __fadd_rn(a, sh[e]);
-            a = __fadd_rn(a, res[e]);
+            if (res_vec) a = __fadd_rn(a, res[e]);
+            else if (rbase && c + e < p.cout) a = __fadd_rn(a, __ldg(rbase + (size_t)pixr[it] * p.cout + c + e));
             if (act == FRCNN_ACT_RELU) a = fmaxf(a, 0.f);
             else if (act == FRCNN_ACT_RELU6) a = fminf(fmaxf(a, 0.f), 6.f);
             y[e] = a;
           }
-          *reinterpret_cast<float4*>(obase + (size_t)pixr[it] * p.cout + c) = make_float4(y[0], y[1], y[2], y[3]);
+          if (vec_ok) {
+            *reinterpret_cast<float4*>(optr) = make_float4(y[0], y[1], y[2], y[3]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) if (c + e < p.cout) optr[e] = y[e];
+          }
         }
       }
-    } else {
-#pragma unroll
-      for (int it = 0; it < ITERS; ++it) {
-        if (pixr[it] < 0 || !col_ok) continue;
-        const int r = it * ROWS_PER_IT + rsub;
-        const float4 v = stage[r * CH + ((cg ^ r) & (CH - 1))];
-        float y[4] = {v.x, v.y, v.z, v.w};
-        float* optr = obase + (size_t)pixr[it] * p.cout + c;
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          float a = y[e];
-          if (scale) a = __fmul_rn(a, sc[e]);
-          if (shift) a = __fadd_rn(a, sh[e]);
-          if (rbase && c + e < p.cout) a = __fadd_rn(a, __ldg(rbase + (size_t)pixr[it] * p.cout + c + e));
-          if (act == FRCNN_ACT_RELU) a = fmaxf(a, 0.f);
-          else if (act == FRCNN_ACT_RELU6) a = fminf(fmaxf(a, 0.f), 6.f);
-          y[e] = a;
-        }
-        if (vec_ok) {
-          *reinterpret_cast<float4*>(optr) = make_float4(y[0], y[1], y[2], y[3]);
-        } else {
-#pragma unroll
-          for (int e = 0; e < 4; ++e) if (c + e < p.cout) optr[e] = y[e];
-        }
-      }
+      if (threadIdx.x == 128) FRCNN_TRACE2(703, 0);
     }
   }
-  if (threadIdx.x == 128) FRCNN_TRACE2(703, 0);
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
-  if (threadIdx.x == 256) FRCNN_TRACE2(704, 0);
+  if (warp == 12) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
+  if (threadIdx.x == 384) FRCNN_TRACE2(704, 0);
 }
 
 // split-K second pass: out = act((sum_z ws[z]) * scale + shift (+ residual)), z summed in index order (deterministic)
@@ -532,10 +549,10 @@ extern "C" int frcnn_conv_plan_create(frcnn_conv_plan** out, const frcnn_conv_de
   int bn = d->block_n;
   if (bn == 0) {
     long best = -1;
-    const int cands[3] = {128, 64, 32};
-    for (int i = 0; i < 3; ++i) {
+    const int cands[2] = {128, 64};
+    for (int i = 0; i < 2; ++i) {
       const int c = cands[i];
-      if (c > 32 && c / 2 >= d->cout) continue;        // tile mostly empty
+      if (c > 64 && c / 2 >= d->cout) continue;        // tile mostly empty
       const long ctas = m_tiles * cdiv(d->cout, c);
       const long waves = (ctas + 147) / 148;
       // measured (profiles/r01): a k-block costs ~1400 cycles whatever block_n is (SS-mode tcgen05.mma is bound by the
@@ -544,7 +561,7 @@ extern "C" int frcnn_conv_plan_create(frcnn_conv_plan** out, const frcnn_conv_de
       if (best < 0 || cost < best) { best = cost; bn = c; }
     }
   }
-  FRCNN_REQUIRE(bn == 32 || bn == 64 || bn == 128, "block_n must be 32, 64 or 128");
+  FRCNN_REQUIRE(bn == 64 || bn == 128, "block_n must be 64 or 128");
 
   // A: NHWC activations as a rank-4 tensor {C, W, H, N}; traversal stride = conv stride on W and H
   {
@@ -602,9 +619,15 @@ extern "C" int frcnn_conv_plan_create(frcnn_conv_plan** out, const frcnn_conv_de
   }
   p->block_n = bn;
   p->stages = RING;
-  p->smem = bn == 128 ? smem_bytes<128>() : bn == 64 ? smem_bytes<64>() : smem_bytes<32>();
+  p->smem = bn == 128 ? smem_bytes<128>() : smem_bytes<64>();
   FRCNN_REQUIRE(m_tiles <= 0x7fffffffL, "too many tiles");
-  p->grid = dim3((unsigned)m_tiles, (unsigned)cdiv(d->cout, bn), (unsigned)splits);
+  k.m_tiles = (int)m_tiles; k.n_tiles = cdiv(d->cout, bn);
+  const long total_units = m_tiles * k.n_tiles * splits;
+  FRCNN_REQUIRE(total_units <= 0x7fffffffL, "too many work units");
+  k.total_units = (int)total_units;
+  int sms = 148;
+  { int dev = 0; cudaDeviceProp pr; if (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&pr, dev) == cudaSuccess && pr.multiProcessorCount > 0) sms = pr.multiProcessorCount; }
+  p->grid = dim3((unsigned)(total_units < sms ? total_units : sms), 1, 1);   // persistent: one CTA per SM walks the units
   *out = p;
   return OK;
 }
@@ -614,8 +637,7 @@ extern "C" int frcnn_conv_plan_run(const frcnn_conv_plan* p, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   switch (p->block_n) {
     case 128: return launch<128>(p, st);
-    case 64: return launch<64>(p, st);
-    default: return launch<32>(p, st);
+    default: return launch<64>(p, st);
   }
 }
 
@@ -626,8 +648,8 @@ extern "C" int frcnn_conv_plan_info(const frcnn_conv_plan* p, int* block_n, int*
   if (tile_n) *tile_n = p->kp.tn;
   if (tile_h) *tile_h = p->kp.th;
   if (tile_w) *tile_w = p->kp.tw;
-  if (grid_m) *grid_m = (int)p->grid.x;
-  if (grid_n) *grid_n = (int)p->grid.y;
+  if (grid_m) *grid_m = p->kp.m_tiles;
+  if (grid_n) *grid_n = p->kp.n_tiles;
   if (stages) *stages = p->splits;   /* reported as "splits": the ring depth is a compile-time constant (4) */
   if (smem) *smem = p->smem;
   return OK;

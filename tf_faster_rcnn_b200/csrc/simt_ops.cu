@@ -27,57 +27,72 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, float* __restri
 }
 
 // ---- first-layer convolution, cin == 3 ------------------------------------------------------------------
-// thread = (output pixel, group of 8 output channels); filter bank staged in shared memory.
-template <int CG>
-__global__ void conv_first_kernel(const float* __restrict__ in, const float* __restrict__ w,
-                                  const float* __restrict__ scale, const float* __restrict__ shift,
-                                  float* __restrict__ out, int n, int h, int wd, int cout, int k, int stride,
-                                  int pad_t, int pad_l, int ho, int wo, int act) {
-  extern __shared__ float wsm[];  // [k*k*3][cout]
-  const int wcount = k * k * 3 * cout;
-  for (int i = threadIdx.x; i < wcount; i += blockDim.x) wsm[i] = w[i];
+// Block = 8x16 output pixels x all output channels.  The input patch and the whole filter bank sit in shared memory;
+// a warp = 32 pixels x one group of 32 output channels, so every weight read is a warp-wide broadcast float4 and each
+// thread keeps 32 accumulators (1 input LDS + 8 weight LDS.128 per 32 FFMA).
+constexpr int CF_TH = 8, CF_TW = 16;
+__global__ void __launch_bounds__(256)
+conv_first_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ scale,
+                  const float* __restrict__ shift, float* __restrict__ out, int h, int wd, int cout, int k, int stride,
+                  int pad_t, int pad_l, int ho, int wo, int act, int tiles_x, int tiles_y) {
+  extern __shared__ float smem_cf[];
+  const int taps = k * k * 3;
+  float* wsm = smem_cf;                                   // [k*k*3][cout]
+  const int ph = (CF_TH - 1) * stride + k, pw = (CF_TW - 1) * stride + k;
+  float* psm = smem_cf + taps * cout;                     // [ph][pw][3]
+  const int tile = blockIdx.x;
+  const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, b = tile / (tiles_x * tiles_y);
+  const int oy0 = ty * CF_TH, ox0 = tx * CF_TW;
+  const int iy0 = oy0 * stride - pad_t, ix0 = ox0 * stride - pad_l;
+  for (int i = threadIdx.x; i < taps * cout; i += blockDim.x) wsm[i] = __ldg(w + i);
+  for (int i = threadIdx.x; i < ph * pw * 3; i += blockDim.x) {
+    const int c = i % 3, x = (i / 3) % pw, y = i / (3 * pw);
+    const int iy = iy0 + y, ix = ix0 + x;
+    psm[i] = (iy >= 0 && iy < h && ix >= 0 && ix < wd) ? __ldg(in + (((size_t)b * h + iy) * wd + ix) * 3 + c) : 0.f;
+  }
   __syncthreads();
-  const int groups = cout / CG;
-  const long total = (long)n * ho * wo * groups;
-  const long gid = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= total) return;
-  const int g = (int)(gid % groups);
-  const long pix = gid / groups;
-  const int ox = (int)(pix % wo);
-  const int oy = (int)((pix / wo) % ho);
-  const int b = (int)(pix / ((long)wo * ho));
-  float acc[CG];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int groups = cout >> 5;                           // 32-channel groups (1 or 2)
+  const int g = warp % groups;
+  const int pblk = warp / groups;                         // 32-pixel block inside the tile
+  const int nblk = (blockDim.x >> 5) / groups;
+  for (int pb = pblk; pb < (CF_TH * CF_TW) / 32; pb += nblk) {
+    const int pix = pb * 32 + lane;
+    const int py = pix / CF_TW, px = pix % CF_TW;
+    float acc[32];
 #pragma unroll
-  for (int i = 0; i < CG; ++i) acc[i] = 0.f;
-  const int iy0 = oy * stride - pad_t, ix0 = ox * stride - pad_l;
-  for (int r = 0; r < k; ++r) {
-    const int iy = iy0 + r;
-    if (iy < 0 || iy >= h) continue;
-    for (int s = 0; s < k; ++s) {
-      const int ix = ix0 + s;
-      if (ix < 0 || ix >= wd) continue;
-      const float* ip = in + (((size_t)b * h + iy) * wd + ix) * 3;
-      const float x0 = __ldg(ip), x1 = __ldg(ip + 1), x2 = __ldg(ip + 2);
-      const float* wp = wsm + ((r * k + s) * 3) * cout + g * CG;
+    for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+    for (int r = 0; r < k; ++r)
+      for (int s2 = 0; s2 < k; ++s2) {
+        const float* ip = psm + ((py * stride + r) * pw + px * stride + s2) * 3;
+        const float* wp = wsm + ((r * k + s2) * 3) * cout + g * 32;
 #pragma unroll
-      for (int i = 0; i < CG; ++i) {
-        acc[i] = fmaf(x0, wp[i], acc[i]);
-        acc[i] = fmaf(x1, wp[cout + i], acc[i]);
-        acc[i] = fmaf(x2, wp[2 * cout + i], acc[i]);
+        for (int c = 0; c < 3; ++c) {
+          const float x = ip[c];
+          const float4* w4 = reinterpret_cast<const float4*>(wp + c * cout);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 wv = w4[j];
+            acc[4 * j + 0] = fmaf(x, wv.x, acc[4 * j + 0]); acc[4 * j + 1] = fmaf(x, wv.y, acc[4 * j + 1]);
+            acc[4 * j + 2] = fmaf(x, wv.z, acc[4 * j + 2]); acc[4 * j + 3] = fmaf(x, wv.w, acc[4 * j + 3]);
+          }
+        }
       }
+    const int oy = oy0 + py, ox = ox0 + px;
+    if (oy < ho && ox < wo) {
+      float* op = out + (((size_t)b * ho + oy) * wo + ox) * cout + g * 32;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        float v = acc[i];
+        const int ch = g * 32 + i;
+        if (scale) v = __fmul_rn(v, __ldg(scale + ch));
+        if (shift) v = __fadd_rn(v, __ldg(shift + ch));
+        acc[i] = apply_act(v, act);
+      }
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(op + i) = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
     }
   }
-  float* op = out + (size_t)pix * cout + g * CG;
-#pragma unroll
-  for (int i = 0; i < CG; ++i) {
-    float v = acc[i];
-    const int c = g * CG + i;
-    if (scale) v = __fmul_rn(v, __ldg(scale + c));
-    if (shift) v = __fadd_rn(v, __ldg(shift + c));
-    acc[i] = apply_act(v, act);
-  }
-#pragma unroll
-  for (int i = 0; i < CG; i += 4) *reinterpret_cast<float4*>(op + i) = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
 }
 
 // ---- depthwise 3x3 ---------------------------------------------------------------------------------------
@@ -330,12 +345,18 @@ extern "C" int frcnn_pack_conv_weights(const float* w, float* hi, float* lo, int
 extern "C" int frcnn_conv_first(const float* in, const float* w, const float* scale, const float* shift, float* out, int n,
                                 int h, int wd, int cout, int k, int stride, int pad_t, int pad_l, int ho, int wo, int act,
                                 void* stream) {
-  FRCNN_REQUIRE(in && w && out && cout % 8 == 0, "conv_first: cout must be a multiple of 8");
-  const size_t smem = (size_t)k * k * 3 * cout * sizeof(float);
-  FRCNN_REQUIRE(smem <= 48 * 1024, "conv_first: filter bank %zu B exceeds 48 KiB", smem);
-  const long total = (long)n * ho * wo * (cout / 8);
-  conv_first_kernel<8><<<blocks_for(total, 256), 256, smem, (cudaStream_t)stream>>>(in, w, scale, shift, out, n, h, wd, cout, k,
-                                                                                  stride, pad_t, pad_l, ho, wo, act);
+  FRCNN_REQUIRE(in && w && out && (cout == 32 || cout == 64), "conv_first: cout must be 32 or 64");
+  const int ph = (CF_TH - 1) * stride + k, pw = (CF_TW - 1) * stride + k;
+  const size_t smem = ((size_t)k * k * 3 * cout + (size_t)ph * pw * 3) * sizeof(float);
+  FRCNN_REQUIRE(smem <= 100 * 1024, "conv_first: %zu B of shared memory needed", smem);
+  static size_t attr_smem = 0;
+  if (smem > 48 * 1024 && smem > attr_smem) {
+    FRCNN_CUDA(cudaFuncSetAttribute(conv_first_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_smem = smem;
+  }
+  const int tiles_x = cdiv(wo, CF_TW), tiles_y = cdiv(ho, CF_TH);
+  conv_first_kernel<<<(unsigned)(tiles_x * tiles_y * n), 256, smem, (cudaStream_t)stream>>>(in, w, scale, shift, out, h, wd, cout, k, stride,
+                                                                                         pad_t, pad_l, ho, wo, act, tiles_x, tiles_y);
   FRCNN_LAUNCH_CHECK();
   return OK;
 }

@@ -212,10 +212,14 @@ class ShapePlan:
         fc7 = net._head_to_tail(t, self.pool5)
         self.fc7 = fc7
 
+        ld_head = (5 * C + 3) // 4 * 4            # zero-padded to a multiple of 4 columns: vector stores + split-K apply
+
         def fused_cls():
             wc, wb = wts[sc + "/cls_score/weights"], wts[sc + "/bbox_pred/weights"]
-            return (np.concatenate([wc, wb], axis=1).reshape(1, 1, wc.shape[0], 5 * C), None,
-                    np.concatenate([wts[sc + "/cls_score/biases"], wts[sc + "/bbox_pred/biases"]]).astype(F))
+            wf = np.zeros((1, 1, wc.shape[0], ld_head), F); bf = np.zeros(ld_head, F)
+            wf[0, 0, :, :C] = wc; wf[0, 0, :, C:5 * C] = wb
+            bf[:C] = wts[sc + "/cls_score/biases"]; bf[C:5 * C] = wts[sc + "/bbox_pred/biases"]
+            return wf, None, bf
         self.head_out = t.fc(fc7, sc + "/cls_bbox", N.ACT_NONE, packed=wts.packed_custom(sc + "/cls_bbox", fused_cls))
         self.cls_score = t.new(R, C); self.cls_prob = t.new(R, C); self.bbox_pred = t.new(R, 4 * C)
         stds, means = cfgd["bbox_stds"], cfgd["bbox_means"]
