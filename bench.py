@@ -65,7 +65,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append([c.strip() for c in out.split(",")])
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.1)
 
     def summary(self):
         sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
@@ -102,8 +102,13 @@ def cpu_reference_step(key, weights, blob, im_info, C, scales, post):
 def all_host_threads():
     """torchrun exports OMP_NUM_THREADS=1; the CPU arm is entitled to every core the process may run on."""
     import torch
-    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    torch.set_num_threads(max(1, n))
+    if os.environ.get("OMP_NUM_THREADS") and "FRCNN_CPU_THREADS" not in os.environ:
+        # forced (torchrun sets 1): fall back to one thread per physical core (SMT siblings make oneDNN convs far slower:
+        # 128 threads on the 64-core host measured 13x slower than 64)
+        n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        torch.set_num_threads(max(1, n // 2 if n > 16 else n))
+    elif "FRCNN_CPU_THREADS" in os.environ:
+        torch.set_num_threads(int(os.environ["FRCNN_CPU_THREADS"]))
     return torch.get_num_threads()
 
 
@@ -306,7 +311,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--net", default="res101", choices=sorted(NETS))

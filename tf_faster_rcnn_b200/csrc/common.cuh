@@ -168,6 +168,10 @@ __device__ __forceinline__ float ld_nc_f32_pinned(const float* p) {
   return v;
 }
 
+// programmatic dependent launch: let the next kernel in the stream start its prologue early / wait for the previous one's data
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // round-to-nearest fp32 -> tf32 (result is an fp32 bit pattern with the low 13 mantissa bits clear)
 __device__ __forceinline__ float to_tf32(float x) {
   uint32_t r;

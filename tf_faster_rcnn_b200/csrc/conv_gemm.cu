@@ -162,11 +162,28 @@ conv_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (threadIdx.x == 0) FRCNN_TRACE2(701, 0);
+  // Programmatic dependent launch: the next kernel of the stream may begin (its prologue and weight prefetch overlap our
+  // tail); we ourselves touch the previous kernel's outputs only behind pdl_wait() (A loads, residual loads, stores).
+  pdl_launch_dependents();
 
   // Every role walks the same unit sequence; ring slots / barrier phases run on across units (kbt, ct are running totals).
   if (warp == 12) {
     if (lane == 0) {
       const int cchunks = p.cin / BLOCK_K;
+      // weights do not depend on the previous kernel: prefetch the first unit's leading B tiles before the dependency wait
+      int b_issued = 0;
+      if ((int)blockIdx.x < p.total_units) {
+        const Unit t0 = decode_unit(p, blockIdx.x, num_kb_total);
+        for (int kb = 0; kb < t0.num_kb && kb < RING; ++kb, ++b_issued) {
+          const int g = t0.kb0 + kb;
+          const int tap = g / cchunks, kc = g - tap * cchunks;
+          mbar_expect_tx(&full[kb], (uint32_t)(2 * kBTile));
+          const int kcoord = tap * p.cin + kc * BLOCK_K;
+          tma_load_2d(smem_b + kb * kBStage, &tmBhi, &full[kb], kcoord, t0.nblk * BN);
+          tma_load_2d(smem_b + kb * kBStage + kBTile, &tmBlo, &full[kb], kcoord, t0.nblk * BN);
+        }
+      }
+      pdl_wait();
       int kbt = 0;
       for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
         const Unit t = decode_unit(p, u, num_kb_total);
@@ -181,12 +198,14 @@ conv_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
           mbar_expect_tx(&a_full[slot], (uint32_t)p.a_box_bytes);
           tma_load_4d(smem_a + slot * A_TILE_BYTES, &tmA, &a_full[slot], kc * BLOCK_K, t.w0 * p.stride + s - p.pad_l,
                       t.h0 * p.stride + r - p.pad_t, t.n0);
-          mbar_wait(&mma_done[slot], par ^ 1u);                // MMAs that read this B slot have completed
-          FRCNN_TRACE(0, kbt);
-          mbar_expect_tx(&full[slot], (uint32_t)(2 * kBTile));
-          const int kcoord = tap * p.cin + kc * BLOCK_K;
-          tma_load_2d(smem_b + slot * kBStage, &tmBhi, &full[slot], kcoord, t.nblk * BN);
-          tma_load_2d(smem_b + slot * kBStage + kBTile, &tmBlo, &full[slot], kcoord, t.nblk * BN);
+          if (kbt >= b_issued) {
+            mbar_wait(&mma_done[slot], par ^ 1u);              // MMAs that read this B slot have completed
+            FRCNN_TRACE(0, kbt);
+            mbar_expect_tx(&full[slot], (uint32_t)(2 * kBTile));
+            const int kcoord = tap * p.cin + kc * BLOCK_K;
+            tma_load_2d(smem_b + slot * kBStage, &tmBhi, &full[slot], kcoord, t.nblk * BN);
+            tma_load_2d(smem_b + slot * kBStage + kBTile, &tmBlo, &full[slot], kcoord, t.nblk * BN);
+          }
           FRCNN_TRACE(1, kbt);
         }
       }
@@ -276,6 +295,7 @@ conv_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     const int q = warp & 3;                   // TMEM lane quarter this warp may access
     const int col0 = ((warp - 4) >> 2) * W;
     const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col0;
+    pdl_wait();                               // residual / output buffers belong to earlier kernels until they completed
     int ct = 0;
     for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
       const Unit t = decode_unit(p, u, num_kb_total);
@@ -406,6 +426,8 @@ conv_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
 __global__ void splitk_reduce_kernel(const float* __restrict__ ws, int splits, long long out_elems, int cout,
                                      const float* __restrict__ scale, const float* __restrict__ shift,
                                      const float* __restrict__ residual, int act, float* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // one float4 (cout % 4 == 0) per thread
   const long long i = i4 * 4;
   if (i >= out_elems) return;
@@ -507,6 +529,13 @@ static void choose_tile(int n, int ho, int wo, int stride, int* tn, int* th, int
   *tn = bn; *th = bh; *tw = bw;
 }
 
+// FRCNN_NO_PDL=1 disables programmatic dependent launch (debug / A-B measurements)
+static bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("FRCNN_NO_PDL"); v = (e && e[0] == '1') ? 0 : 1; }
+  return v == 1;
+}
+
 template <int BN>
 static int launch(const frcnn_conv_plan* p, cudaStream_t st) {
   static bool attr_done = false;
@@ -514,13 +543,21 @@ static int launch(const frcnn_conv_plan* p, cudaStream_t st) {
     FRCNN_CUDA(cudaFuncSetAttribute(conv_gemm_tf32x3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<BN>()));
     attr_done = true;
   }
-  conv_gemm_tf32x3_kernel<BN><<<p->grid, NUM_THREADS, smem_bytes<BN>(), st>>>(p->tmA, p->tmBhi, p->tmBlo, p->kp);
-  FRCNN_LAUNCH_CHECK();
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  const bool pdl = pdl_enabled();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = p->grid; cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = smem_bytes<BN>(); cfg.stream = st;
+  cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+  FRCNN_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_tf32x3_kernel<BN>, p->tmA, p->tmBhi, p->tmBlo, p->kp));
   if (p->splits > 1) {
     const long long n4 = p->kp.out_elems / 4;
-    splitk_reduce_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(p->ws, p->splits, p->kp.out_elems, p->kp.cout, p->scale, p->shift,
-                                                                      p->residual, p->act, p->out);
-    FRCNN_LAUNCH_CHECK();
+    cudaLaunchConfig_t rc{};
+    rc.gridDim = dim3((unsigned)((n4 + 255) / 256)); rc.blockDim = dim3(256); rc.dynamicSmemBytes = 0; rc.stream = st;
+    rc.attrs = attr; rc.numAttrs = pdl ? 1 : 0;
+    FRCNN_CUDA(cudaLaunchKernelEx(&rc, splitk_reduce_kernel, (const float*)p->ws, p->splits, p->kp.out_elems, p->kp.cout, p->scale, p->shift,
+                                  p->residual, p->act, p->out));
   }
   return OK;
 }
