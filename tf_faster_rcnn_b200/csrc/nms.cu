@@ -5,10 +5,10 @@
 //   `_nms` ABI  : lib/nms/gpu_nms.hpp:1-2                                        -> frcnn_nms_host
 //
 // Algorithm (replaces nms_kernel.cu's N x N/64 bitmask + host sweep, which is O(N^2) work and memory even
-// though at most post_nms_top_n boxes survive): candidates are walked in priority order in chunks of 256.
-// For one chunk the CTA (a) tests every candidate against the <=K boxes already kept (kept set lives in shared
-// memory), (b) builds the 256x256 intra-chunk suppression bitmask, (c) one thread resolves the chunk
-// sequentially with 4 x 64-bit words; survivors are appended to the kept set.  The walk stops as soon as
+// though at most post_nms_top_n boxes survive): candidates are walked in priority order in windows of 1024.
+// Per round the CTA (a) tests every candidate of the window against the <=K boxes already kept (kept set in shared
+// memory) and compacts the survivors, (b) builds the <=256x256 suppression bitmask among them, (c) one thread resolves
+// it sequentially with 4 x 64-bit words; survivors are appended to the kept set.  The walk stops as soon as
 // max_out boxes are kept, so the RPN stage touches only the first few thousand of the 17k-50k anchors.
 // IoU arithmetic is the oracle's op-by-op fp32 sequence (__f*_rn: no FMA contraction) for all three predicate
 // variants (flags), so survivor indices are bit-exact.
@@ -48,49 +48,71 @@ __device__ __forceinline__ bool suppresses(const float4 a, float area_a, const f
   return (flags & FRCNN_NMS_INCLUSIVE) ? (ovr >= thr) : (ovr > thr);
 }
 
+constexpr int WIDE = 1024;    // candidates filtered against the kept set per round (one per thread)
+
 struct GreedyShared {
   unsigned long long mask[CHUNK][CHUNK / 64];
   float4 cbox[CHUNK];
   float carea[CHUNK];
-  int dead[CHUNK];
+  int cpos[CHUNK];                 // position (in priority order) of each compacted candidate
+  int warp_cnt[WIDE / 32];
+  unsigned char chunk_kept[CHUNK];
   int nkept;
-  int chunk_kept[CHUNK];
   int chunk_nk;
+  int n_alive;                     // compacted candidates this round (<= CHUNK)
+  int consumed;                    // candidates of the window that are settled after this round
 };
 
-// CTA-cooperative greedy NMS over `m` candidates given in priority order.
+// CTA-cooperative greedy NMS over `m` candidates given in priority order (blockDim.x == 1024).
 //   cand(i) -> float4 box of the i-th candidate;  kept/kept_area: storage for the kept set (shared or global)
-//   kept_pos: positions (0..m-1) of survivors.   returns number kept (in sh.nkept, valid after the final barrier)
+//   kept_pos: positions (0..m-1) of survivors.   Number kept is left in sh.nkept (valid after the final barrier).
+// Round: (a) a window of up to 1024 candidates is tested against the kept set, one candidate per thread; the survivors are
+// compacted in order (at most CHUNK = 256 of them -- the window is cut right after the 256th survivor and the rest is
+// re-examined next round), (b) the CHUNK x CHUNK suppression bitmask among the survivors is built, (c) one thread resolves it
+// sequentially with 4 x 64-bit words, skipping suppressed candidates with ffs.  With a low keep rate (RPN: most anchors
+// overlap something already kept) almost everything dies in (a) and a round settles ~1000 candidates.
 template <typename CandFn>
 __device__ void block_greedy_nms(CandFn cand, int m, float thr, unsigned flags, int max_out, float4* kept, float* kept_area,
                                  int* kept_pos, GreedyShared& sh) {
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) sh.nkept = 0;
   __syncthreads();
-  for (int base = 0; base < m; base += CHUNK) {
-    const int cn = min(CHUNK, m - base);
+  int base = 0;
+  while (base < m) {
     const int nk = sh.nkept;
     if (nk >= max_out) break;
-    if (tid < CHUNK) {
-      sh.dead[tid] = 0;
-      if (tid < cn) {
-        const float4 b = canon(cand(base + tid), flags);
-        sh.cbox[tid] = b;
-        sh.carea[tid] = box_area(b, flags);
-      }
+    const int wn = min(WIDE, m - base);
+    // (a) filter the window against the kept set
+    bool alive = false;
+    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+    float ab = 0.f;
+    if (tid < wn) {
+      b = canon(cand(base + tid), flags);
+      ab = box_area(b, flags);
+      alive = true;
+      if (thr >= 0.f)
+        for (int k = 0; k < nk; ++k)
+          if (suppresses(kept[k], kept_area[k], b, ab, thr, flags)) { alive = false; break; }
     }
+    // ordered compaction: exclusive prefix of `alive` over the block
+    const unsigned bal = __ballot_sync(0xffffffffu, alive);
+    if (lane == 0) sh.warp_cnt[warp] = __popc(bal);
     __syncthreads();
-    // (a) candidates vs kept set: 4 threads per candidate stride over the kept boxes
+    int before = 0;
+    for (int w = 0; w < warp; ++w) before += sh.warp_cnt[w];
+    const int idx = before + __popc(bal & ((1u << lane) - 1u));
+    if (tid == 0) {
+      int tot = 0;
+      for (int w = 0; w < WIDE / 32; ++w) tot += sh.warp_cnt[w];
+      sh.n_alive = min(tot, CHUNK);
+      if (tot <= CHUNK) sh.consumed = wn;
+    }
+    if (alive && idx < CHUNK) { sh.cbox[idx] = b; sh.carea[idx] = ab; sh.cpos[idx] = base + tid; }
+    if (alive && idx == CHUNK) sh.consumed = tid;          // first survivor that does not fit: the window is cut here
+    __syncthreads();
+    const int cn = sh.n_alive;
+    // (b) suppression bitmask among the survivors: thread (row i, 64-bit word wj); only j > i matters
     if (thr >= 0.f) {
-      const int c = tid >> 2, part = tid & 3;
-      if (c < cn) {
-        const float4 b = sh.cbox[c];
-        const float ab = sh.carea[c];
-        bool d = false;
-        for (int k = part; k < nk && !d; k += 4) d = suppresses(kept[k], kept_area[k], b, ab, thr, flags);
-        if (d) sh.dead[c] = 1;
-      }
-      // (b) intra-chunk bitmask: thread (row i, 64-bit word wj); only j > i matters
       const int i = tid >> 2, wj = tid & 3;
       if (i < cn) {
         unsigned long long bits = 0ull;
@@ -103,19 +125,28 @@ __device__ void block_greedy_nms(CandFn cand, int m, float thr, unsigned flags, 
       }
     }
     __syncthreads();
-    // (c) sequential resolve of the chunk
+    // (c) sequential resolve (ffs skips suppressed candidates)
     if (tid == 0) {
       static_assert(CHUNK == 256, "resolve loop is written for 4 x 64-bit words");
-      unsigned long long r0 = 0ull, r1 = 0ull, r2 = 0ull, r3 = 0ull;
+      unsigned long long rem[4] = {0ull, 0ull, 0ull, 0ull};
       int k = nk, ck = 0;
-      for (int i = 0; i < cn && k < max_out; ++i) {
-        if (sh.dead[i]) continue;
-        const int w = i >> 6;
-        const unsigned long long cur = w == 0 ? r0 : w == 1 ? r1 : w == 2 ? r2 : r3;
-        if ((cur >> (i & 63)) & 1ull) continue;
-        sh.chunk_kept[ck++] = i;
-        ++k;
-        if (thr >= 0.f) { r0 |= sh.mask[i][0]; r1 |= sh.mask[i][1]; r2 |= sh.mask[i][2]; r3 |= sh.mask[i][3]; }
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        const int lim = min(64, cn - w * 64);
+        if (lim <= 0) break;
+        const unsigned long long valid = lim == 64 ? ~0ull : ((1ull << lim) - 1ull);
+        unsigned long long todo = ~rem[w] & valid;
+        while (todo && k < max_out) {
+          const int bit = __ffsll((long long)todo) - 1;
+          const int i = w * 64 + bit;
+          sh.chunk_kept[ck++] = (unsigned char)i;
+          ++k;
+          if (thr >= 0.f) {
+#pragma unroll
+            for (int w2 = 0; w2 < 4; ++w2) if (w2 >= w) rem[w2] |= sh.mask[i][w2];
+          }
+          todo = (todo & ~rem[w]) & ~((2ull << bit) - 1ull);
+        }
       }
       sh.chunk_nk = ck;
     }
@@ -125,10 +156,12 @@ __device__ void block_greedy_nms(CandFn cand, int m, float thr, unsigned flags, 
       const int i = sh.chunk_kept[tid];
       kept[nk + tid] = sh.cbox[i];
       kept_area[nk + tid] = sh.carea[i];
-      kept_pos[nk + tid] = base + i;
+      kept_pos[nk + tid] = sh.cpos[i];
     }
+    const int consumed = sh.consumed;
     __syncthreads();
     if (tid == 0) sh.nkept = nk + ck;
+    base += consumed;
     __syncthreads();
   }
   __syncthreads();
