@@ -61,6 +61,7 @@ struct GreedyShared {
   int chunk_nk;
   int n_alive;                     // compacted candidates this round (<= CHUNK)
   int consumed;                    // candidates of the window that are settled after this round
+  int tot_alive, last_wn;          // survivors / size of the previous window (drives threads-per-candidate)
 };
 
 // CTA-cooperative greedy NMS over `m` candidates given in priority order (blockDim.x == 1024).
@@ -75,25 +76,31 @@ template <typename CandFn>
 __device__ void block_greedy_nms(CandFn cand, int m, float thr, unsigned flags, int max_out, float4* kept, float* kept_area,
                                  int* kept_pos, GreedyShared& sh) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) sh.nkept = 0;
+  if (tid == 0) { sh.nkept = 0; sh.tot_alive = WIDE; sh.last_wn = WIDE; }
   __syncthreads();
   int base = 0;
   while (base < m) {
     const int nk = sh.nkept;
     if (nk >= max_out) break;
-    const int wn = min(WIDE, m - base);
+    // threads per candidate: when most of the last window survived (high keep rate) a round can only settle ~256 candidates,
+    // so look at 256 with 4 threads each; when few survive, look at 1024 with one thread each.
+    const int tpc = (sh.tot_alive * 3 >= sh.last_wn) ? 4 : 1;
+    const int wn = min(WIDE / tpc, m - base);
+    const int ci = tid / tpc, part = tid % tpc;
     // (a) filter the window against the kept set
-    bool alive = false;
+    bool dead = false;
     float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
     float ab = 0.f;
-    if (tid < wn) {
-      b = canon(cand(base + tid), flags);
+    if (ci < wn) {
+      b = canon(cand(base + ci), flags);
       ab = box_area(b, flags);
-      alive = true;
       if (thr >= 0.f)
-        for (int k = 0; k < nk; ++k)
-          if (suppresses(kept[k], kept_area[k], b, ab, thr, flags)) { alive = false; break; }
+        for (int k = part; k < nk; k += tpc)
+          if (suppresses(kept[k], kept_area[k], b, ab, thr, flags)) { dead = true; break; }
     }
+    const unsigned dbal = __ballot_sync(0xffffffffu, dead);
+    const bool any_dead = tpc == 1 ? dead : (((dbal >> (lane & ~3)) & 0xFu) != 0u);
+    const bool alive = (ci < wn) && part == 0 && !any_dead;       // one representative thread per candidate
     // ordered compaction: exclusive prefix of `alive` over the block
     const unsigned bal = __ballot_sync(0xffffffffu, alive);
     if (lane == 0) sh.warp_cnt[warp] = __popc(bal);
@@ -105,10 +112,11 @@ __device__ void block_greedy_nms(CandFn cand, int m, float thr, unsigned flags, 
       int tot = 0;
       for (int w = 0; w < WIDE / 32; ++w) tot += sh.warp_cnt[w];
       sh.n_alive = min(tot, CHUNK);
+      sh.tot_alive = tot; sh.last_wn = wn;
       if (tot <= CHUNK) sh.consumed = wn;
     }
-    if (alive && idx < CHUNK) { sh.cbox[idx] = b; sh.carea[idx] = ab; sh.cpos[idx] = base + tid; }
-    if (alive && idx == CHUNK) sh.consumed = tid;          // first survivor that does not fit: the window is cut here
+    if (alive && idx < CHUNK) { sh.cbox[idx] = b; sh.carea[idx] = ab; sh.cpos[idx] = base + ci; }
+    if (alive && idx == CHUNK) sh.consumed = ci;           // first survivor that does not fit: the window is cut here
     __syncthreads();
     const int cn = sh.n_alive;
     // (b) suppression bitmask among the survivors: thread (row i, 64-bit word wj); only j > i matters
