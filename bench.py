@@ -271,6 +271,11 @@ def run_ours(args):
     conv_alg_flops = plan.tape.conv_flops
     conv_tflops = conv_alg_flops * n_steps / (ms_conv / 1000.0) / 1e12
     peak = pk.get("bf16_tflops_sustained", pk.get("bf16_tflops"))
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r01_conv_traffic.json")
+    if args.net == "res101" and os.path.exists(tp):           # from the committed ncu capture of `bench.py --ncu` (same workload)
+        with open(tp) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch_avg")
     launches_per_image = len(plan.tape.steps) + 4
     line = {
         "metric": "images/sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": n_steps, "warmup": max(args.warmup, 3),
@@ -284,7 +289,8 @@ def run_ours(args):
         "gpu_launches": launches_per_image * n_steps,
         "clocks": sampler.summary() if sampler else None,
         "roofline": {"bound": "tensor", "kernel": "conv_gemm_tf32x3_kernel (all %d conv/FC launches of one image)" % len(conv_steps),
-                     "achieved": conv_tflops, "peak": peak, "unit": "TFLOP/s", "frac": conv_tflops / peak, "traffic": None,
+                     "achieved": conv_tflops, "peak": peak, "unit": "TFLOP/s", "frac": conv_tflops / peak, "traffic": traffic,
+                     "traffic_note": "dram__bytes_read+write per conv launch, averaged over the 106 launches of one image (profiles/r01_conv_traffic.json)",
                      "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (%s); 3xTF32 issues 3 TF32 MMAs per product, so its own "
                                     "ceiling is (TF32 peak)/3 ~ bf16 peak/6" % pk_src,
                      "algorithmic_gflop_per_image": conv_alg_flops / 1e9, "conv_ms_per_image": ms_conv / n_steps,
