@@ -127,6 +127,12 @@ int frcnn_max_pool(const float* in_dev, float* out_dev, int n, int h, int w, int
 /* mean over the spatial positions: [r, hw, c] -> [r, c]  (tf.reduce_mean axis=[1,2]) */
 int frcnn_spatial_mean(const float* in_dev, float* out_dev, int r, int hw, int c, void* stream);
 
+/* image -> network blob on the device (lib/model/test.py:26-58 for one scale): blob[y,x,c] = bilinear resize, with OpenCV's
+ * INTER_LINEAR float arithmetic, of (float32(img) - means) ; img_dev uint8 BGR [h0,w0,3]; blob_dev fp32 [H,W,3] with
+ * H = cvRound(h0*fy), W = cvRound(w0*fx) computed by the caller.  means3 is a HOST pointer. */
+int frcnn_preprocess(const unsigned char* img_dev, int h0, int w0, const double* means3, double fx, double fy,
+                     float* blob_dev, int H, int W, void* stream);
+
 /* RPN: 2-way softmax (fg prob), anchor generation, bbox_transform_inv, clip -- proposal_layer.py:62-69.
  * rpn_out_dev: [hw, ld] rows with the 2A class logits at column 0 and the 4A deltas at column delta_col
  * (delta_col % 4 == 0, ld % 4 == 0: the fused 1x1 RPN head writes both).

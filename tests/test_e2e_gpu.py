@@ -101,3 +101,93 @@ def test_im_detect_and_fused_detect(cuda):
     for j in range(1, 21):
         assert np.array_equal(per_class[j], want[j]), j
         assert np.array_equal(loop[j], want[j]), j
+
+
+def _run_modes(net_name, C, scales, hw, cfg_updates, oracle_opts):
+    from model.config import cfg
+    saved = {}
+    try:
+        for k, v in cfg_updates.items():
+            node = cfg
+            *parents, leaf = k.split(".")
+            for p_ in parents:
+                node = node[p_]
+            saved[k] = node[leaf]
+            node[leaf] = v
+        net, w = build(net_name, C, scales)
+        blob = synth.synthetic_blob(*hw)
+        im_info = np.array([hw[0], hw[1], 1.0], F)
+        st = P.test_image(net_name, w, blob, im_info, C, P.opts(anchor_scales=scales, **oracle_opts))
+        out = net.test_image(None, blob, im_info)
+        return net, st, out
+    finally:
+        for k, v in saved.items():
+            node = cfg
+            *parents, leaf = k.split(".")
+            for p_ in parents:
+                node = node[p_]
+            node[leaf] = v
+
+
+def test_top_mode_end_to_end(cuda):
+    """TEST.MODE='top' (proposal_top_layer_tf): 5000 RoIs by score, no NMS -- through the whole net."""
+    net, st, (cls_score, cls_prob, bbox_pred, rois) = _run_modes(
+        "mobile", 21, (8, 16, 32), (224, 320), {"TEST.MODE": "top", "TEST.RPN_TOP_N": 1000}, dict(test_mode="top", rpn_top_n=1000))
+    assert rois.shape == (1000, 5) and st["rois"].shape == (1000, 5)
+    plan = net.plan_for(224, 320)
+    keep = plan.roi_keep.cpu().numpy()
+    common, ia, ib = np.intersect1d(keep, st["roi_keep"], return_indices=True)
+    assert len(common) >= 990
+    assert np.abs(cls_prob[ia] - st["cls_prob"][ib]).max() < 1e-4 and np.abs(bbox_pred[ia] - st["bbox_pred"][ib]).max() < 1e-4
+
+
+@pytest.mark.parametrize("gpu_pred", [False, True])
+def test_non_e2e_proposal_mode_end_to_end(cuda, gpu_pred):
+    """USE_E2E_TF=False (proposal_layer: pre-NMS top 6000 + '+1' NMS with the cpu_nms / gpu_nms predicate)."""
+    net, st, (cls_score, cls_prob, bbox_pred, rois) = _run_modes(
+        "res50", 21, (8, 16, 32), (210, 333), {"USE_E2E_TF": False, "USE_GPU_NMS": gpu_pred}, dict(use_e2e_tf=False, use_gpu_nms=gpu_pred))
+    plan = net.plan_for(210, 333)
+    keep = plan.roi_keep.cpu().numpy()[:rois.shape[0]]
+    common, ia, ib = np.intersect1d(keep, st["roi_keep"], return_indices=True)
+    assert abs(rois.shape[0] - st["rois"].shape[0]) <= 3 and len(common) >= 0.97 * len(st["roi_keep"])
+    assert np.abs(cls_prob[ia] - st["cls_prob"][ib]).max() < 1e-4 and np.abs(bbox_pred[ia] - st["bbox_pred"][ib]).max() < 1e-4
+
+
+def test_cfg5_shape_resnet152_1000_proposals(cuda):
+    """config 5 geometry at a reduced image size: ResNet-152, anchor scales (2,4,8,16,32) (A=15), 1000 proposals."""
+    net, st, (cls_score, cls_prob, bbox_pred, rois) = _run_modes(
+        "res152", 81, (2, 4, 8, 16, 32), (256, 352), {"TEST.RPN_POST_NMS_TOP_N": 1000}, dict(rpn_post_nms_top_n=1000))
+    plan = net.plan_for(256, 352)
+    keep = plan.roi_keep.cpu().numpy()[:rois.shape[0]]
+    common, ia, ib = np.intersect1d(keep, st["roi_keep"], return_indices=True)
+    print("\n[cfg5-shape] rois gpu %d oracle %d common %d" % (rois.shape[0], st["rois"].shape[0], len(common)))
+    assert len(common) >= 0.97 * len(st["roi_keep"])
+    assert np.abs(cls_prob[ia] - st["cls_prob"][ib]).max() < 1e-4 and np.abs(bbox_pred[ia] - st["bbox_pred"][ib]).max() < 1e-4
+
+
+def test_shape_cache_and_repeatability(cuda):
+    """Two blob shapes through one network (plan cache) and bit-identical repeated runs (CUDA graph replay, split-K)."""
+    net, w = build("res50", 21, (8, 16, 32))
+    a = synth.synthetic_blob(208, 320, 1); b = synth.synthetic_blob(240, 272, 2)
+    r1 = net.test_image(None, a, np.array([208, 320, 1.0], F))
+    r2 = net.test_image(None, b, np.array([240, 272, 1.0], F))
+    r3 = net.test_image(None, a, np.array([208, 320, 1.0], F))
+    assert len(net._plans) == 2
+    for x, y in zip(r1, r3):
+        assert np.array_equal(x, y)
+    assert r2[3].shape[1] == 5
+
+
+def test_im_detect_with_device_preprocess(cuda):
+    """Opt-in device blob (frcnn_preprocess) gives the same detections as the host OpenCV blob (inputs differ <= 1e-4)."""
+    import cv2
+    import model.test as MT
+    net, w = build("res50", 21, (8, 16, 32))
+    im = cv2.blur(np.random.default_rng(5).integers(0, 256, (240, 320, 3), dtype=np.uint8), (5, 5))
+    s0, b0 = MT.im_detect(None, net, im)
+    MT.DEVICE_PREPROCESS = True
+    try:
+        s1, b1 = MT.im_detect(None, net, im)
+    finally:
+        MT.DEVICE_PREPROCESS = False
+    assert s0.shape == s1.shape and np.abs(s0 - s1).max() < 1e-3 and np.abs(b0 - b1).max() < 0.5

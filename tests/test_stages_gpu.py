@@ -324,3 +324,21 @@ def test_nms_host_vs_reference_kernel(cuda):
             fn(keep.ctypes.data_as(N.ip), ctypes.byref(num), sd.ctypes.data_as(N.fp), n, 5, thr, 0)
             got = ops.nms_host(sd, thr, N.NMS_MODE_GPU_NMS)
             assert np.array_equal(got, keep[:num.value]), (n, thr)
+
+
+@pytest.mark.parametrize("hw", [(375, 500), (480, 640), (333, 1200), (601, 799)])
+def test_device_preprocess_matches_opencv(cuda, hw):
+    """frcnn_preprocess vs the host path (float32(im) - PIXEL_MEANS, cv2.resize INTER_LINEAR): same blob size, <= 1e-4."""
+    from tf_faster_rcnn_b200 import ops
+    from model.test import _get_image_blob, blob_geometry
+    from model.config import cfg
+    rng = np.random.default_rng(hw[0])
+    im = rng.integers(0, 256, hw + (3,), dtype=np.uint8)
+    want, scales = _get_image_blob(im)
+    H, W, f = blob_geometry(im.shape)
+    assert (H, W) == want.shape[1:3] and f == scales[0]
+    blob = torch.empty((1, H, W, 3), dtype=torch.float32, device="cuda")
+    ops.preprocess(dev(im), np.asarray(cfg.PIXEL_MEANS).ravel(), f, f, blob)
+    err = np.abs(blob.cpu().numpy() - want).max()
+    print("\n[preprocess %dx%d -> %dx%d] max abs diff vs OpenCV %.2e" % (hw[0], hw[1], H, W, err))
+    assert err < 1e-4

@@ -44,6 +44,7 @@ SIGNATURES = {
     "frcnn_depthwise3x3": (ci, [vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp]),
     "frcnn_max_pool": (ci, [vp, vp, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp]),
     "frcnn_spatial_mean": (ci, [vp, vp, ci, ci, ci, vp]),
+    "frcnn_preprocess": (ci, [vp, ci, ci, C.POINTER(C.c_double), C.c_double, C.c_double, vp, ci, ci, vp]),
     "frcnn_rpn_decode": (ci, [vp, ci, ci, vp, ci, ci, ci, ci, cf, cf, vp, vp, vp]),
     "frcnn_sort_workspace_bytes": (sz, [ci]),
     "frcnn_sort_desc": (ci, [vp, ci, vp, vp, vp, sz, vp]),

@@ -325,6 +325,38 @@ __global__ void bbox_decode_kernel(const float* __restrict__ rois, const float* 
   reinterpret_cast<float4*>(pred)[i] = o;
 }
 
+// ---- image -> blob on the device: mean subtraction + cv2.resize(INTER_LINEAR) restated ----------
+// lib/model/test.py:35-36 (float32(pixel) - PIXEL_MEANS, evaluated in double and rounded once, as numpy's in-place
+// float32 -= float64 does) followed by OpenCV's float bilinear resize: source coordinate (dx + 0.5) / fx - 0.5 in double,
+// cast to float, floor, clamp; horizontal pass then vertical pass.
+__global__ void preprocess_kernel(const unsigned char* __restrict__ img, int h0, int w0, double m0, double m1, double m2,
+                                  double inv_fx, double inv_fy, float* __restrict__ blob, int H, int W) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= H * W) return;
+  const int dx = i % W, dy = i / W;
+  float fx = (float)((dx + 0.5) * inv_fx - 0.5);
+  int sx = (int)floorf(fx); fx -= (float)sx;
+  if (sx < 0) { fx = 0.f; sx = 0; }
+  if (sx >= w0 - 1) { fx = 0.f; sx = w0 - 1; }
+  float fy = (float)((dy + 0.5) * inv_fy - 0.5);
+  int sy = (int)floorf(fy); fy -= (float)sy;
+  if (sy < 0) { fy = 0.f; sy = 0; }
+  if (sy >= h0 - 1) { fy = 0.f; sy = h0 - 1; }
+  const int sx1 = min(sx + 1, w0 - 1), sy1 = min(sy + 1, h0 - 1);
+  const float a0 = 1.f - fx, a1 = fx, b0 = 1.f - fy, b1 = fy;
+  const double mean[3] = {m0, m1, m2};
+  const unsigned char* r0 = img + (size_t)sy * w0 * 3;
+  const unsigned char* r1 = img + (size_t)sy1 * w0 * 3;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float v00 = (float)((double)r0[sx * 3 + c] - mean[c]), v01 = (float)((double)r0[sx1 * 3 + c] - mean[c]);
+    const float v10 = (float)((double)r1[sx * 3 + c] - mean[c]), v11 = (float)((double)r1[sx1 * 3 + c] - mean[c]);
+    const float t0 = __fadd_rn(__fmul_rn(v00, a0), __fmul_rn(v01, a1));
+    const float t1 = __fadd_rn(__fmul_rn(v10, a0), __fmul_rn(v11, a1));
+    blob[(size_t)i * 3 + c] = __fadd_rn(__fmul_rn(t0, b0), __fmul_rn(t1, b1));
+  }
+}
+
 static inline unsigned blocks_for(long total, int threads) { return (unsigned)((total + threads - 1) / threads); }
 
 }  // namespace frcnn
@@ -425,6 +457,15 @@ extern "C" int frcnn_bbox_decode(const float* rois, const float* bbox_pred, int 
   FRCNN_REQUIRE(rois && bbox_pred && pred_boxes, "bbox_decode: null pointer");
   bbox_decode_kernel<<<blocks_for((long)r * num_classes, 256), 256, 0, (cudaStream_t)stream>>>(
       rois, bbox_pred, r, num_classes, im_scale, (float)(orig_w - 1), (float)(orig_h - 1), pred_boxes);
+  FRCNN_LAUNCH_CHECK();
+  return OK;
+}
+
+extern "C" int frcnn_preprocess(const unsigned char* img_dev, int h0, int w0, const double* means3, double fx, double fy,
+                                float* blob_dev, int H, int W, void* stream) {
+  FRCNN_REQUIRE(img_dev && means3 && blob_dev && h0 > 0 && w0 > 0 && H > 0 && W > 0 && fx > 0 && fy > 0, "preprocess: bad argument");
+  preprocess_kernel<<<blocks_for((long)H * W, 256), 256, 0, (cudaStream_t)stream>>>(img_dev, h0, w0, means3[0], means3[1], means3[2],
+                                                                                  1.0 / fx, 1.0 / fy, blob_dev, H, W);
   FRCNN_LAUNCH_CHECK();
   return OK;
 }

@@ -115,6 +115,15 @@ def spatial_mean(x, out):
     N.check(N.lib().frcnn_spatial_mean(_p(_f32(x)), _p(_f32(out)), r, hw, c, _stream()), "spatial_mean")
 
 
+def preprocess(img_u8_dev, means3, fx, fy, blob):
+    """uint8 BGR [h0,w0,3] (device) -> mean-subtracted, bilinearly resized fp32 blob [1,H,W,3] (device)."""
+    h0, w0, _ = img_u8_dev.shape
+    _, H, W, _ = blob.shape
+    m = (C.c_double * 3)(*[float(v) for v in means3])
+    N.check(N.lib().frcnn_preprocess(C.c_void_p(img_u8_dev.data_ptr()), h0, w0, m, float(fx), float(fy), _p(blob), H, W, _stream()),
+            "preprocess")
+
+
 def rpn_decode(rpn_out, delta_col, base_anchors, num_anchors, fh, fw, im_h, im_w, scores, props, feat_stride=16):
     ld = rpn_out.shape[-1]
     N.check(N.lib().frcnn_rpn_decode(_p(_f32(rpn_out)), ld, delta_col, _p(base_anchors), num_anchors, fh, fw, feat_stride,
