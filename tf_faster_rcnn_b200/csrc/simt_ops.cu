@@ -328,18 +328,21 @@ __global__ void bbox_decode_kernel(const float* __restrict__ rois, const float* 
 // ---- image -> blob on the device: mean subtraction + cv2.resize(INTER_LINEAR) restated ----------
 // lib/model/test.py:35-36 (float32(pixel) - PIXEL_MEANS, evaluated in double and rounded once, as numpy's in-place
 // float32 -= float64 does) followed by OpenCV's float bilinear resize: source coordinate (dx + 0.5) / fx - 0.5 in double,
-// cast to float, floor, clamp; horizontal pass then vertical pass.
+// floor + fraction in double, clamp; horizontal pass then vertical pass.
 __global__ void preprocess_kernel(const unsigned char* __restrict__ img, int h0, int w0, double m0, double m1, double m2,
                                   double inv_fx, double inv_fy, float* __restrict__ blob, int H, int W) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= H * W) return;
   const int dx = i % W, dy = i / W;
-  float fx = (float)((dx + 0.5) * inv_fx - 0.5);
-  int sx = (int)floorf(fx); fx -= (float)sx;
+  // source coordinate and its fractional part in double, rounded to float once (OpenCV 4.x; measured against cv2 4.13:
+  // taking the fraction of the float32 coordinate is off by up to 6e-3 on the blob)
+  const double cx = (dx + 0.5) * inv_fx - 0.5, cy = (dy + 0.5) * inv_fy - 0.5;
+  int sx = (int)floor(cx);
+  float fx = (float)(cx - (double)sx);
   if (sx < 0) { fx = 0.f; sx = 0; }
   if (sx >= w0 - 1) { fx = 0.f; sx = w0 - 1; }
-  float fy = (float)((dy + 0.5) * inv_fy - 0.5);
-  int sy = (int)floorf(fy); fy -= (float)sy;
+  int sy = (int)floor(cy);
+  float fy = (float)(cy - (double)sy);
   if (sy < 0) { fy = 0.f; sy = 0; }
   if (sy >= h0 - 1) { fy = 0.f; sy = h0 - 1; }
   const int sx1 = min(sx + 1, w0 - 1), sy1 = min(sy + 1, h0 - 1);
