@@ -294,69 +294,63 @@ class_nms_kernel(const float* __restrict__ probs, const float4* __restrict__ pre
   }
 }
 
-// single CTA: k-th largest kept score by 4-pass radix select (scores > 0 => uint order == float order), then
-// filter (score >= image_thresh, ties kept: test.py:176-180) and emit compact records.
+// single CTA: max_per_image cap + record emission (test.py:173-180).  Every class list is sorted by descending score, so
+// (1) count_c(t) = #scores >= t is a binary search per class, (2) the k-th largest kept score overall is found by a bitwise
+// search on the fp32 pattern (scores > 0 => unsigned order == float order; 32 rounds of 80 parallel binary searches + a block
+// reduction), (3) "keep score >= image_thresh" just truncates each list to count_c(thresh) (ties kept, as the reference).
+__device__ __forceinline__ int count_ge(const float* __restrict__ sorted_desc, int n, unsigned tbits) {
+  int lo = 0, hi = n;                       // first index whose score < t
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (__float_as_uint(sorted_desc[mid]) >= tbits) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
 __global__ void __launch_bounds__(NMS_THREADS, 1)
 cap_emit_kernel(const float4* __restrict__ pred, int r, int C, int max_per_image, int max_det, int* __restrict__ keep,
                 int* __restrict__ keep_cnt, const float* __restrict__ keep_score, float* __restrict__ det, int* __restrict__ ndet) {
-  __shared__ unsigned hist[256];
-  __shared__ unsigned s_prefix, s_kth;
+  __shared__ int s_warp[NMS_THREADS / 32];
   __shared__ int s_total;
   __shared__ int s_off[1025];
-  const int tid = threadIdx.x;
-  if (tid == 0) {
-    int t = 0;
-    for (int c = 1; c < C; ++c) t += keep_cnt[c];
-    s_total = t;
-  }
-  __syncthreads();
-  const int total = s_total;
-  unsigned thresh_bits = 0u;   // keep everything
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool is_cls = tid >= 1 && tid < C;
+  const int my_cnt = is_cls ? keep_cnt[tid] : 0;
+  const float* my_scores = keep_score + (size_t)tid * r;
+  auto block_sum = [&](int v) -> int {
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if (lane == 0) s_warp[warp] = v;
+    __syncthreads();
+    if (tid == 0) { int t = 0; for (int w = 0; w < NMS_THREADS / 32; ++w) t += s_warp[w]; s_total = t; }
+    __syncthreads();
+    return s_total;
+  };
+  const int total = block_sum(my_cnt);
+  int new_cnt = my_cnt;
   if (max_per_image > 0 && total > max_per_image) {
-    unsigned prefix = 0u; int kth = max_per_image;   // kth largest, 1-based
-    for (int pass = 3; pass >= 0; --pass) {
-      if (tid < 256) hist[tid] = 0u;
-      __syncthreads();
-      const unsigned hi_mask = pass == 3 ? 0u : (0xffffffffu << ((pass + 1) * 8));
-      for (int i = tid; i < (C - 1) * r; i += blockDim.x) {
-        const int c = 1 + i / r, j = i % r;
-        if (j < keep_cnt[c]) {
-          const unsigned u = __float_as_uint(keep_score[(size_t)c * r + j]);
-          if ((u & hi_mask) == (prefix & hi_mask)) atomicAdd(&hist[(u >> (pass * 8)) & 255u], 1u);
-        }
-      }
-      __syncthreads();
-      if (tid == 0) {
-        int acc = 0; int b = 255;
-        for (; b >= 0; --b) { if (acc + (int)hist[b] >= kth) break; acc += (int)hist[b]; }
-        s_prefix = prefix | ((unsigned)b << (pass * 8));
-        s_kth = (unsigned)(kth - acc);
-      }
-      __syncthreads();
-      prefix = s_prefix; kth = (int)s_kth;
-      __syncthreads();
+    unsigned t = 0u;                                   // largest pattern with count(score >= t) >= max_per_image
+    for (int bit = 31; bit >= 0; --bit) {
+      const unsigned cand = t | (1u << bit);
+      const int cnt = block_sum(is_cls ? count_ge(my_scores, my_cnt, cand) : 0);
+      if (cnt >= max_per_image) t = cand;
     }
-    thresh_bits = prefix;
+    if (is_cls) new_cnt = count_ge(my_scores, my_cnt, t);
   }
-  // filter each class list in place (order preserved), thread per class
-  if (tid < C && tid >= 1) {
-    const int cnt = keep_cnt[tid];
-    int o = 0;
-    for (int j = 0; j < cnt; ++j) {
-      const unsigned u = __float_as_uint(keep_score[(size_t)tid * r + j]);
-      if (u >= thresh_bits) { keep[(size_t)tid * r + o] = keep[(size_t)tid * r + j]; ++o; }
-    }
-    for (int j = o; j < cnt; ++j) keep[(size_t)tid * r + j] = -1;
-    keep_cnt[tid] = o;
+  if (is_cls) {
+    for (int j = new_cnt; j < my_cnt; ++j) keep[(size_t)tid * r + j] = -1;
+    keep_cnt[tid] = new_cnt;
   }
+  // exclusive prefix of the per-class counts (C <= 1024: one thread per class, warp scan + warp totals)
+  int v = is_cls ? new_cnt : 0, incl = v;
+  for (int o = 1; o < 32; o <<= 1) { const int n = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += n; }
   __syncthreads();
-  if (tid == 0) {
-    int acc = 0;
-    s_off[0] = 0; s_off[1] = 0;
-    for (int c = 1; c < C; ++c) { s_off[c] = acc; acc += keep_cnt[c]; }
-    s_off[C] = acc;
-    *ndet = acc < max_det ? acc : max_det;
-  }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  int before = 0;
+  for (int w = 0; w < warp; ++w) before += s_warp[w];
+  if (tid <= C) s_off[tid] = before + incl - v;
+  if (tid == NMS_THREADS - 1) { const int all = before + incl; *ndet = all < max_det ? all : max_det; }
   __syncthreads();
   for (int i = tid; i < (C - 1) * r; i += blockDim.x) {
     const int c = 1 + i / r, j = i % r;
@@ -367,24 +361,9 @@ cap_emit_kernel(const float4* __restrict__ pred, int r, int C, int max_per_image
         const float4 b = __ldg(pred + (size_t)roi * C + c);
         float* d = det + (size_t)slot * 6;
         d[0] = b.x; d[1] = b.y; d[2] = b.z; d[3] = b.w;
-        d[4] = 0.f; d[5] = (float)c;
+        d[4] = keep_score[(size_t)c * r + j]; d[5] = (float)c;
       }
     }
-  }
-}
-
-// scores for the records are re-read from probs to avoid depending on the (compacted) keep_score order
-__global__ void fill_det_scores_kernel(const float* __restrict__ probs, int C, const int* __restrict__ keep, const int* __restrict__ keep_cnt,
-                                       int r, int max_det, float* __restrict__ det) {
-  // thread per class walks its list; offsets recomputed by prefix over keep_cnt (C is tiny)
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c < 1 || c >= C) return;
-  int off = 0;
-  for (int k = 1; k < c; ++k) off += keep_cnt[k];
-  for (int j = 0; j < keep_cnt[c]; ++j) {
-    const int slot = off + j;
-    if (slot >= max_det) break;
-    det[(size_t)slot * 6 + 4] = __ldg(probs + (size_t)keep[(size_t)c * r + j] * C + c);
   }
 }
 
@@ -497,8 +476,6 @@ extern "C" int frcnn_detect_post(const float* cls_prob, const float* pred_boxes,
   FRCNN_LAUNCH_CHECK();
   cap_emit_kernel<<<1, NMS_THREADS, 0, st>>>(reinterpret_cast<const float4*>(pred_boxes), r, num_classes, max_per_image, max_det,
                                             keep, keep_cnt, keep_score, det, ndet);
-  FRCNN_LAUNCH_CHECK();
-  fill_det_scores_kernel<<<cdiv(num_classes, 128), 128, 0, st>>>(cls_prob, num_classes, keep, keep_cnt, r, max_det, det);
   FRCNN_LAUNCH_CHECK();
   return OK;
 }

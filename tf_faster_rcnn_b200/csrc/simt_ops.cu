@@ -190,61 +190,74 @@ __device__ __forceinline__ float exp_cr(float x) { return (float)exp((double)x);
 
 __device__ __forceinline__ float lerp_rn(float a, float b, float t) { return __fadd_rn(a, __fmul_rn(__fsub_rn(b, a), t)); }
 
-__device__ __forceinline__ float4 bilinear4(const float* __restrict__ feat, int fh, int fw, int c, int cg, float in_y,
-                                            float in_x) {
-  if (in_y < 0.f || in_y > (float)(fh - 1) || in_x < 0.f || in_x > (float)(fw - 1)) return make_float4(0.f, 0.f, 0.f, 0.f);
-  const float ty = floorf(in_y), lx = floorf(in_x);
-  const int top = (int)ty, bot = (int)ceilf(in_y), lef = (int)lx, rig = (int)ceilf(in_x);
-  const float yl = __fsub_rn(in_y, ty), xl = __fsub_rn(in_x, lx);
-  const float4 tl = __ldg(reinterpret_cast<const float4*>(feat + ((size_t)top * fw + lef) * c) + cg);
-  const float4 tr = __ldg(reinterpret_cast<const float4*>(feat + ((size_t)top * fw + rig) * c) + cg);
-  const float4 bl = __ldg(reinterpret_cast<const float4*>(feat + ((size_t)bot * fw + lef) * c) + cg);
-  const float4 br = __ldg(reinterpret_cast<const float4*>(feat + ((size_t)bot * fw + rig) * c) + cg);
+// One block per (RoI, output row): the first threads compute the sampling geometry of that row once (the per-sample
+// divisions and float index math used to be redone by every channel thread and made the kernel ALU bound), then all threads
+// stream channels: 4 gathers + lerps per sample, float4 wide.
+struct CropSample { int top, bot, lef, rig; float yl, xl; int valid; };
+
+__device__ __forceinline__ float4 sample4(const float* __restrict__ feat, int fw, int c, int cg, const CropSample& s) {
+  if (!s.valid) return make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 tl = __ldg(reinterpret_cast<const float4*>(feat + ((size_t)s.top * fw + s.lef) * c) + cg);
+  const float4 tr = __ldg(reinterpret_cast<const float4*>(feat + ((size_t)s.top * fw + s.rig) * c) + cg);
+  const float4 bl = __ldg(reinterpret_cast<const float4*>(feat + ((size_t)s.bot * fw + s.lef) * c) + cg);
+  const float4 br = __ldg(reinterpret_cast<const float4*>(feat + ((size_t)s.bot * fw + s.rig) * c) + cg);
   float4 o;
-  o.x = lerp_rn(lerp_rn(tl.x, tr.x, xl), lerp_rn(bl.x, br.x, xl), yl);
-  o.y = lerp_rn(lerp_rn(tl.y, tr.y, xl), lerp_rn(bl.y, br.y, xl), yl);
-  o.z = lerp_rn(lerp_rn(tl.z, tr.z, xl), lerp_rn(bl.z, br.z, xl), yl);
-  o.w = lerp_rn(lerp_rn(tl.w, tr.w, xl), lerp_rn(bl.w, br.w, xl), yl);
+  o.x = lerp_rn(lerp_rn(tl.x, tr.x, s.xl), lerp_rn(bl.x, br.x, s.xl), s.yl);
+  o.y = lerp_rn(lerp_rn(tl.y, tr.y, s.xl), lerp_rn(bl.y, br.y, s.xl), s.yl);
+  o.z = lerp_rn(lerp_rn(tl.z, tr.z, s.xl), lerp_rn(bl.z, br.z, s.xl), s.yl);
+  o.w = lerp_rn(lerp_rn(tl.w, tr.w, s.xl), lerp_rn(bl.w, br.w, s.xl), s.yl);
   return o;
 }
 
-__global__ void crop_pool_kernel(const float* __restrict__ feat, int fh, int fw, int c, const float* __restrict__ rois,
-                                 int r, int pooled, int pre_pool, float* __restrict__ out) {
+constexpr int CROP_MAX_POOLED = 16;
+
+__global__ void __launch_bounds__(256)
+crop_pool_kernel(const float* __restrict__ feat, int fh, int fw, int c, const float* __restrict__ rois, int r, int pooled,
+                 int pre_pool, float* __restrict__ out) {
+  __shared__ CropSample smp[CROP_MAX_POOLED * 4];           // [px][dy*2+dx] (one entry per px when !pre_pool)
+  const int ri = blockIdx.x / pooled, py = blockIdx.x % pooled;
+  const int nsub = pre_pool ? 4 : 1;
+  if (threadIdx.x < pooled * nsub) {
+    const int px = threadIdx.x / nsub, sub = threadIdx.x % nsub;
+    const float* roi = rois + (size_t)ri * 5;
+    // network.py:146-153: normalise by (dim-1)*16, then crop_and_resize's own un-normalisation -- op by op as the oracle
+    const float hh = __fmul_rn(__fsub_rn((float)fh, 1.f), 16.f);
+    const float ww = __fmul_rn(__fsub_rn((float)fw, 1.f), 16.f);
+    const float x1 = __fdiv_rn(__ldg(roi + 1), ww), y1 = __fdiv_rn(__ldg(roi + 2), hh);
+    const float x2 = __fdiv_rn(__ldg(roi + 3), ww), y2 = __fdiv_rn(__ldg(roi + 4), hh);
+    const int crop = pre_pool ? 2 * pooled : pooled;
+    const float hs = __fdiv_rn(__fmul_rn(__fsub_rn(y2, y1), (float)(fh - 1)), (float)(crop - 1));
+    const float ws = __fdiv_rn(__fmul_rn(__fsub_rn(x2, x1), (float)(fw - 1)), (float)(crop - 1));
+    const int iy = pre_pool ? 2 * py + (sub >> 1) : py, ix = pre_pool ? 2 * px + (sub & 1) : px;
+    const float in_y = __fadd_rn(__fmul_rn(y1, (float)(fh - 1)), __fmul_rn((float)iy, hs));
+    const float in_x = __fadd_rn(__fmul_rn(x1, (float)(fw - 1)), __fmul_rn((float)ix, ws));
+    CropSample sp;
+    sp.valid = !(in_y < 0.f || in_y > (float)(fh - 1) || in_x < 0.f || in_x > (float)(fw - 1));
+    const float ty = floorf(in_y), lx = floorf(in_x);
+    sp.top = (int)ty; sp.bot = (int)ceilf(in_y); sp.lef = (int)lx; sp.rig = (int)ceilf(in_x);
+    sp.yl = __fsub_rn(in_y, ty); sp.xl = __fsub_rn(in_x, lx);
+    if (!sp.valid) { sp.top = sp.bot = sp.lef = sp.rig = 0; }
+    smp[px * 4 + sub] = sp;
+  }
+  __syncthreads();
   const int c4 = c >> 2;
-  const long total = (long)r * pooled * pooled * c4;
-  const long gid = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= total) return;
-  const int cg = (int)(gid % c4);
-  long t = gid / c4;
-  const int px = (int)(t % pooled); t /= pooled;
-  const int py = (int)(t % pooled);
-  const int ri = (int)(t / pooled);
-  const float* roi = rois + (size_t)ri * 5;
-  // network.py:146-153: normalise by (dim-1)*16, then crop_and_resize's own un-normalisation
-  const float hh = __fmul_rn(__fsub_rn((float)fh, 1.f), 16.f);
-  const float ww = __fmul_rn(__fsub_rn((float)fw, 1.f), 16.f);
-  const float x1 = __fdiv_rn(__ldg(roi + 1), ww), y1 = __fdiv_rn(__ldg(roi + 2), hh);
-  const float x2 = __fdiv_rn(__ldg(roi + 3), ww), y2 = __fdiv_rn(__ldg(roi + 4), hh);
-  const int crop = pre_pool ? 2 * pooled : pooled;
-  const float hs = __fdiv_rn(__fmul_rn(__fsub_rn(y2, y1), (float)(fh - 1)), (float)(crop - 1));
-  const float ws = __fdiv_rn(__fmul_rn(__fsub_rn(x2, x1), (float)(fw - 1)), (float)(crop - 1));
-  const float by = __fmul_rn(y1, (float)(fh - 1)), bx = __fmul_rn(x1, (float)(fw - 1));
-  float4 o;
-  if (!pre_pool) {
-    o = bilinear4(feat, fh, fw, c, cg, __fadd_rn(by, __fmul_rn((float)py, hs)), __fadd_rn(bx, __fmul_rn((float)px, ws)));
-  } else {
-    const float ninf = __int_as_float(0xff800000);
-    o = make_float4(ninf, ninf, ninf, ninf);
+  float* orow = out + (size_t)((size_t)ri * pooled + py) * pooled * c;
+  for (int i = threadIdx.x; i < pooled * c4; i += blockDim.x) {
+    const int px = i / c4, cg = i - px * c4;
+    float4 o;
+    if (!pre_pool) {
+      o = sample4(feat, fw, c, cg, smp[px * 4]);
+    } else {
+      const float ninf = __int_as_float(0xff800000);
+      o = make_float4(ninf, ninf, ninf, ninf);
 #pragma unroll
-    for (int dy = 0; dy < 2; ++dy)
-#pragma unroll
-      for (int dx = 0; dx < 2; ++dx) {
-        const float4 v = bilinear4(feat, fh, fw, c, cg, __fadd_rn(by, __fmul_rn((float)(2 * py + dy), hs)),
-                                   __fadd_rn(bx, __fmul_rn((float)(2 * px + dx), ws)));
+      for (int sub = 0; sub < 4; ++sub) {
+        const float4 v = sample4(feat, fw, c, cg, smp[px * 4 + sub]);
         o.x = fmaxf(o.x, v.x); o.y = fmaxf(o.y, v.y); o.z = fmaxf(o.z, v.z); o.w = fmaxf(o.w, v.w);
       }
+    }
+    reinterpret_cast<float4*>(orow + (size_t)px * c)[cg] = o;
   }
-  reinterpret_cast<float4*>(out + (size_t)(((size_t)ri * pooled + py) * pooled + px) * c)[cg] = o;
 }
 
 // ---- RPN decode ---------------------------------------------------------------------------------------------
@@ -425,9 +438,8 @@ extern "C" int frcnn_spatial_mean(const float* in, float* out, int r, int hw, in
 
 extern "C" int frcnn_crop_pool(const float* feat, int fh, int fw, int c, const float* rois, int r, int pooled, int pre_pool,
                                float* out, void* stream) {
-  FRCNN_REQUIRE(feat && rois && out && c % 4 == 0 && pooled > 1, "crop_pool: bad argument");
-  const long total = (long)r * pooled * pooled * (c / 4);
-  crop_pool_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(feat, fh, fw, c, rois, r, pooled, pre_pool, out);
+  FRCNN_REQUIRE(feat && rois && out && c % 4 == 0 && pooled > 1 && pooled <= CROP_MAX_POOLED, "crop_pool: bad argument");
+  crop_pool_kernel<<<(unsigned)(r * pooled), 256, 0, (cudaStream_t)stream>>>(feat, fh, fw, c, rois, r, pooled, pre_pool, out);
   FRCNN_LAUNCH_CHECK();
   return OK;
 }
