@@ -68,10 +68,13 @@ struct ConvKernelParams {
   int act;
   int a_box_bytes;
   int kb_per_chunk;   // k-blocks accumulated in TMEM before promotion to registers
-  int kb_per_split;   // split-K: split z handles k-blocks [z*kb_per_split, ...); == total when not split
-  int m_tiles, n_tiles, total_units;   // persistent loop: unit u = mt + m_tiles*(nblk + n_tiles*z)
-  float* ws;          // split-K workspace [splits][out elements] (raw partial sums) or NULL
-  long long out_elems;
+  // Work units.  Tiles t = mt + m_tiles*nblk.  Units [0, n_full) are whole tiles (direct epilogue).  The remaining
+  // `n_tail` tiles -- the ragged last round of the persistent loop, or every tile of a layer too small to fill the GPU --
+  // are each split over `splits` units along K: unit n_full + v -> tile n_full + v / splits, split v % splits, which writes
+  // its raw partial tile to ws[(v / splits)][v % splits][128][BN]; tail_reduce_kernel sums them in index order.
+  int kb_per_split;
+  int m_tiles, n_tiles, total_units, n_full, splits;
+  float* ws;
   long long* trace;   // debug: clock64() stamps of CTA (0,0)'s pipeline hand-offs; normally NULL
 };
 
@@ -103,20 +106,21 @@ __device__ __forceinline__ uint64_t sw128_desc(uint32_t saddr) {
 
 // Work unit u (persistent loop: u = blockIdx.x, += gridDim.x) -> output tile + split-K range.
 struct Unit {
-  int w0, h0, n0, nblk, z, kb0, num_kb;
+  int w0, h0, n0, nblk, z, kb0, num_kb, slot;   // slot >= 0: tail tile index (raw partial output), -1: whole tile
 };
 __device__ __forceinline__ Unit decode_unit(const ConvKernelParams& p, int u, int num_kb_total) {
   Unit t;
-  const int mt = u % p.m_tiles;
-  const int rest = u / p.m_tiles;
-  t.nblk = rest % p.n_tiles;
-  t.z = rest / p.n_tiles;
+  int tile;
+  if (u < p.n_full) { tile = u; t.z = 0; t.slot = -1; }
+  else { const int v = u - p.n_full; t.slot = v / p.splits; t.z = v - t.slot * p.splits; tile = p.n_full + t.slot; }
+  const int mt = tile % p.m_tiles;
+  t.nblk = tile / p.m_tiles;
   const int tile_w = mt % p.tiles_w;
   const int tile_h = (mt / p.tiles_w) % p.tiles_h;
   const int tile_n = mt / (p.tiles_w * p.tiles_h);
   t.w0 = tile_w * p.tw; t.h0 = tile_h * p.th; t.n0 = tile_n * p.tn;
-  t.kb0 = t.z * p.kb_per_split;
-  t.num_kb = min(p.kb_per_split, num_kb_total - t.kb0);
+  if (t.slot < 0) { t.kb0 = 0; t.num_kb = num_kb_total; }
+  else { t.kb0 = t.z * p.kb_per_split; t.num_kb = min(p.kb_per_split, num_kb_total - t.kb0); }
   return t;
 }
 
@@ -347,16 +351,35 @@ conv_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       const int dh = rem / p.tw, dw = rem % p.tw;
       const int n = t.n0 + dn, h = t.h0 + dh, w = t.w0 + dw;
       const bool valid = (row < p.tn * rows_img) && n < p.nimg && h < p.ho && w < p.wo;
-      const int my_pix = valid ? (int)(((long long)n * p.ho + h) * p.wo + w) : -1;
       const int cg = lane & (CH - 1);                         // column group of this lane
       const int rsub = lane >> 3;
+      if (t.slot >= 0) {
+        // split tile: plain partial sums in the tile-local [128][BN] workspace layout; the epilogue runs in tail_reduce_kernel
+        float* const wbase = p.ws + ((size_t)t.slot * p.splits + t.z) * (size_t)(BLOCK_M * BN) + (size_t)(q * 32) * BN + col0;
+#pragma unroll
+        for (int pass = 0; pass < W / 32; ++pass) {
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < CH; ++j) {
+            const int a0 = pass * 32 + 4 * j;
+            stage[lane * CH + ((j ^ lane) & (CH - 1))] = make_float4(acc[a0], acc[a0 + 1], acc[a0 + 2], acc[a0 + 3]);
+          }
+          __syncwarp();
+#pragma unroll
+          for (int it = 0; it < ITERS; ++it) {
+            const int r = it * ROWS_PER_IT + rsub;
+            *reinterpret_cast<float4*>(wbase + (size_t)r * BN + pass * 32 + cg * 4) = stage[r * CH + ((cg ^ r) & (CH - 1))];
+          }
+        }
+        continue;
+      }
+      const int my_pix = valid ? (int)(((long long)n * p.ho + h) * p.wo + w) : -1;
       const bool vec_ok = (p.cout & 3) == 0;
-      const bool raw = p.ws != nullptr;                       // split-K: plain partial sums, epilogue runs in the reduce kernel
-      float* const obase = raw ? p.ws + (size_t)t.z * p.out_elems : p.out;
-      const float* const rbase = raw ? nullptr : p.residual;
-      const float* const scale = raw ? nullptr : p.scale;
-      const float* const shift = raw ? nullptr : p.shift;
-      const int act = raw ? FRCNN_ACT_NONE : p.act;
+      float* const obase = p.out;
+      const float* const rbase = p.residual;
+      const float* const scale = p.scale;
+      const float* const shift = p.shift;
+      const int act = p.act;
       int pixr[ITERS];
 #pragma unroll
       for (int it = 0; it < ITERS; ++it) pixr[it] = __shfl_sync(0xffffffffu, my_pix, it * ROWS_PER_IT + rsub);
@@ -422,35 +445,65 @@ conv_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   if (threadIdx.x == 384) FRCNN_TRACE2(704, 0);
 }
 
-// split-K second pass: out = act((sum_z ws[z]) * scale + shift (+ residual)), z summed in index order (deterministic)
-__global__ void splitk_reduce_kernel(const float* __restrict__ ws, int splits, long long out_elems, int cout,
-                                     const float* __restrict__ scale, const float* __restrict__ shift,
-                                     const float* __restrict__ residual, int act, float* __restrict__ out) {
+// Second pass for split tiles: out = act((sum_z ws[slot][z]) * scale + shift (+ residual)), z summed in index order
+// (deterministic).  One block per (tail tile, group of 256/(BN/4) rows); thread = (row, 4 channels).
+template <int BN>
+__global__ void __launch_bounds__(256)
+tail_reduce_kernel(const ConvKernelParams p) {
   pdl_launch_dependents();
   pdl_wait();
-  const long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // one float4 (cout % 4 == 0) per thread
-  const long long i = i4 * 4;
-  if (i >= out_elems) return;
-  float4 a = __ldg(reinterpret_cast<const float4*>(ws + i));
-  for (int z = 1; z < splits; ++z) {
-    const float4 b = __ldg(reinterpret_cast<const float4*>(ws + (size_t)z * out_elems + i));
-    a.x = __fadd_rn(a.x, b.x); a.y = __fadd_rn(a.y, b.y); a.z = __fadd_rn(a.z, b.z); a.w = __fadd_rn(a.w, b.w);
-  }
-  const int c = (int)(i % cout);
-  float y[4] = {a.x, a.y, a.z, a.w};
-  float r4[4] = {0.f, 0.f, 0.f, 0.f};
-  if (residual) { const float4 rv = __ldg(reinterpret_cast<const float4*>(residual + i)); r4[0] = rv.x; r4[1] = rv.y; r4[2] = rv.z; r4[3] = rv.w; }
+  constexpr int RPB = 256 / (BN / 4);                 // rows per block: one (row, 4-channel group) per thread
+  constexpr int GROUPS = BLOCK_M / RPB;
+  const int slot = blockIdx.x / GROUPS, rgroup = blockIdx.x % GROUPS;
+  const int tile = p.n_full + slot;
+  const int mt = tile % p.m_tiles, nblk = tile / p.m_tiles;
+  const int tile_w = mt % p.tiles_w, tile_h = (mt / p.tiles_w) % p.tiles_h, tile_n = mt / (p.tiles_w * p.tiles_h);
+  const int rows_img = p.th * p.tw;
+  constexpr int C4 = BN / 4;
+  static_assert(256 % C4 == 0, "each thread keeps one fixed channel group");
+  const float* base = p.ws + (size_t)slot * p.splits * (size_t)(BLOCK_M * BN);
+  const bool vec_ok = (p.cout & 3) == 0;
+  const int cg = threadIdx.x % C4;
+  const int c = nblk * BN + cg * 4;
+  if (c >= p.cout) return;
+  float sc[4] = {1.f, 1.f, 1.f, 1.f}, sh[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    float v = y[e];
-    if (scale) v = __fmul_rn(v, __ldg(scale + c + e));
-    if (shift) v = __fadd_rn(v, __ldg(shift + c + e));
-    if (residual) v = __fadd_rn(v, r4[e]);
-    if (act == FRCNN_ACT_RELU) v = fmaxf(v, 0.f);
-    else if (act == FRCNN_ACT_RELU6) v = fminf(fmaxf(v, 0.f), 6.f);
-    y[e] = v;
+  for (int e = 0; e < 4; ++e)
+    if (c + e < p.cout) {
+      if (p.scale) sc[e] = __ldg(p.scale + c + e);
+      if (p.shift) sh[e] = __ldg(p.shift + c + e);
+    }
+  {
+    const int row = rgroup * RPB + threadIdx.x / C4;
+    const int dn = row / rows_img, rem = row % rows_img;
+    const int n = tile_n * p.tn + dn, h = tile_h * p.th + rem / p.tw, w = tile_w * p.tw + rem % p.tw;
+    if (row >= p.tn * rows_img || n >= p.nimg || h >= p.ho || w >= p.wo) return;
+    const size_t o = ((((size_t)n * p.ho + h) * p.wo + w)) * p.cout + c;
+    float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.residual) {
+      if (vec_ok) rv = __ldg(reinterpret_cast<const float4*>(p.residual + o));
+      else { float t[4] = {0.f, 0.f, 0.f, 0.f}; for (int e = 0; e < 4; ++e) if (c + e < p.cout) t[e] = __ldg(p.residual + o + e); rv = make_float4(t[0], t[1], t[2], t[3]); }
+    }
+    float4 a = __ldg(reinterpret_cast<const float4*>(base + (size_t)row * BN) + cg);
+    for (int z = 1; z < p.splits; ++z) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(base + ((size_t)z * BLOCK_M + row) * BN) + cg);
+      a.x = __fadd_rn(a.x, b.x); a.y = __fadd_rn(a.y, b.y); a.z = __fadd_rn(a.z, b.z); a.w = __fadd_rn(a.w, b.w);
+    }
+    float y[4] = {a.x, a.y, a.z, a.w};
+    const float res[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float v = y[e];
+      if (p.scale) v = __fmul_rn(v, sc[e]);
+      if (p.shift) v = __fadd_rn(v, sh[e]);
+      if (p.residual) v = __fadd_rn(v, res[e]);
+      if (p.act == FRCNN_ACT_RELU) v = fmaxf(v, 0.f);
+      else if (p.act == FRCNN_ACT_RELU6) v = fminf(fmaxf(v, 0.f), 6.f);
+      y[e] = v;
+    }
+    if (vec_ok) *reinterpret_cast<float4*>(p.out + o) = make_float4(y[0], y[1], y[2], y[3]);
+    else for (int e = 0; e < 4; ++e) if (c + e < p.cout) p.out[o + e] = y[e];
   }
-  *reinterpret_cast<float4*>(out + i) = make_float4(y[0], y[1], y[2], y[3]);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -499,12 +552,8 @@ struct frcnn_conv_plan {
   ConvKernelParams kp;
   int block_n, stages, smem;
   dim3 grid;
-  int splits;
-  float* ws;               // owned split-K workspace
-  // reduce-pass arguments (the GEMM pass sees NULL epilogue inputs when split)
-  const float *scale, *shift, *residual;
-  float* out;
-  int act;
+  int n_tail;
+  float* ws;               // owned workspace of the split tiles
 };
 
 // choose the tile of output pixels (tn x th x tw <= 128) that needs the fewest tiles
@@ -551,13 +600,11 @@ static int launch(const frcnn_conv_plan* p, cudaStream_t st) {
   cfg.gridDim = p->grid; cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = smem_bytes<BN>(); cfg.stream = st;
   cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
   FRCNN_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_tf32x3_kernel<BN>, p->tmA, p->tmBhi, p->tmBlo, p->kp));
-  if (p->splits > 1) {
-    const long long n4 = p->kp.out_elems / 4;
+  if (p->n_tail > 0) {
     cudaLaunchConfig_t rc{};
-    rc.gridDim = dim3((unsigned)((n4 + 255) / 256)); rc.blockDim = dim3(256); rc.dynamicSmemBytes = 0; rc.stream = st;
+    rc.gridDim = dim3((unsigned)(p->n_tail * (BLOCK_M / (256 / (BN / 4))))); rc.blockDim = dim3(256); rc.dynamicSmemBytes = 0; rc.stream = st;
     rc.attrs = attr; rc.numAttrs = pdl ? 1 : 0;
-    FRCNN_CUDA(cudaLaunchKernelEx(&rc, splitk_reduce_kernel, (const float*)p->ws, p->splits, p->kp.out_elems, p->kp.cout, p->scale, p->shift,
-                                  p->residual, p->act, p->out));
+    FRCNN_CUDA(cudaLaunchKernelEx(&rc, tail_reduce_kernel<BN>, p->kp));
   }
   return OK;
 }
@@ -628,43 +675,43 @@ extern "C" int frcnn_conv_plan_create(frcnn_conv_plan** out, const frcnn_conv_de
   k.a_box_bytes = tn * th * tw * BLOCK_K * 4;
   k.kb_per_chunk = d->kb_per_chunk > 0 ? d->kb_per_chunk : 8;
   k.trace = nullptr;
-  k.out_elems = (long long)d->n * d->ho * d->wo * d->cout;
-  // split-K (deterministic two-pass) when the output tiling alone leaves most of the 148 SMs idle
-  const long ctas = m_tiles * cdiv(d->cout, bn);
-  int splits = d->split_k;
-  if (splits == 0) {
-    splits = 1;
-    if (ctas <= 74 && num_kb >= 16 && (d->cout & 3) == 0) {
-      splits = (int)(148 / ctas);
-      if (splits > num_kb / 8) splits = num_kb / 8;
-      if (splits > 8) splits = 8;
-      if (splits < 1) splits = 1;
-    }
+  // ---- work decomposition: whole tiles + K-split tail (see ConvKernelParams) ------------------------------------------
+  int sms = 148;
+  { int dev = 0; cudaDeviceProp pr; if (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&pr, dev) == cudaSuccess && pr.multiProcessorCount > 0) sms = pr.multiProcessorCount; }
+  k.m_tiles = (int)m_tiles; k.n_tiles = cdiv(d->cout, bn);
+  const long tiles = m_tiles * k.n_tiles;
+  FRCNN_REQUIRE(tiles <= 0x3fffffffL, "too many tiles");
+  long n_tail = 0; int splits = 1;
+  const int max_split = num_kb / 8 < 8 ? num_kb / 8 : 8;        // >= 8 k-blocks (one chunk) per split, at most 8 splits
+  if (d->split_k > 1) {                                         // forced: every tile is split
+    n_tail = tiles; splits = d->split_k;
+  } else if (d->split_k == 0 && max_split >= 2) {
+    const long rem = tiles % sms;
+    // measured (r01): a split unit still pays ~7 us of per-unit overhead and the reduce pass ~10 us, so the ragged round is
+    // only worth splitting when the K loop is long (>= 48 k-blocks); small layers gain from 16 k-blocks on.
+    if (tiles <= sms / 2) { if (num_kb >= 16) { n_tail = tiles; splits = (int)(sms / tiles); } }  // layer too small to fill the GPU
+    else if (tiles > sms && rem > 0 && rem <= sms / 2 && num_kb >= 48) { n_tail = rem; splits = (int)(sms / rem); }   // ragged last round
+    if (splits > max_split) splits = max_split;
+    if (splits < 2) { n_tail = 0; splits = 1; }
   }
-  FRCNN_REQUIRE(splits >= 1 && splits <= 64 && (splits == 1 || (d->cout & 3) == 0), "bad split_k");
   int kbs = cdiv(num_kb, splits);
-  kbs = cdiv(kbs, k.kb_per_chunk) * k.kb_per_chunk;        // whole chunks per split
+  kbs = cdiv(kbs, k.kb_per_chunk) * k.kb_per_chunk;            // whole chunks per split
   splits = cdiv(num_kb, kbs);
-  k.kb_per_split = kbs;
-  k.ws = nullptr;
-  p->splits = splits; p->ws = nullptr;
-  p->scale = d->scale_dev; p->shift = d->shift_dev; p->residual = d->residual_dev; p->out = d->out_dev; p->act = d->act;
-  if (splits > 1) {
-    cudaError_t e = cudaMalloc(&p->ws, (size_t)splits * k.out_elems * sizeof(float));
-    if (e != cudaSuccess) { free(p); return cuda_fail(e, "split-K workspace", __FILE__, __LINE__); }
+  if (splits < 2) { n_tail = 0; splits = 1; }
+  k.kb_per_split = kbs; k.splits = splits; k.n_full = (int)(tiles - n_tail);
+  const long total_units = (tiles - n_tail) + n_tail * splits;
+  FRCNN_REQUIRE(total_units <= 0x7fffffffL, "too many work units");
+  k.total_units = (int)total_units;
+  k.ws = nullptr; p->ws = nullptr; p->n_tail = (int)n_tail;
+  if (n_tail > 0) {
+    cudaError_t e = cudaMalloc(&p->ws, (size_t)n_tail * splits * BLOCK_M * bn * sizeof(float));
+    if (e != cudaSuccess) { free(p); return cuda_fail(e, "split-tile workspace", __FILE__, __LINE__); }
     k.ws = p->ws;
   }
+  p->grid = dim3((unsigned)(total_units < sms ? total_units : sms), 1, 1);   // persistent: one CTA per SM walks the units
   p->block_n = bn;
   p->stages = RING;
   p->smem = bn == 128 ? smem_bytes<128>() : smem_bytes<64>();
-  FRCNN_REQUIRE(m_tiles <= 0x7fffffffL, "too many tiles");
-  k.m_tiles = (int)m_tiles; k.n_tiles = cdiv(d->cout, bn);
-  const long total_units = m_tiles * k.n_tiles * splits;
-  FRCNN_REQUIRE(total_units <= 0x7fffffffL, "too many work units");
-  k.total_units = (int)total_units;
-  int sms = 148;
-  { int dev = 0; cudaDeviceProp pr; if (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&pr, dev) == cudaSuccess && pr.multiProcessorCount > 0) sms = pr.multiProcessorCount; }
-  p->grid = dim3((unsigned)(total_units < sms ? total_units : sms), 1, 1);   // persistent: one CTA per SM walks the units
   *out = p;
   return OK;
 }
@@ -687,7 +734,7 @@ extern "C" int frcnn_conv_plan_info(const frcnn_conv_plan* p, int* block_n, int*
   if (tile_w) *tile_w = p->kp.tw;
   if (grid_m) *grid_m = p->kp.m_tiles;
   if (grid_n) *grid_n = p->kp.n_tiles;
-  if (stages) *stages = p->splits;   /* reported as "splits": the ring depth is a compile-time constant (4) */
+  if (stages) *stages = p->n_tail > 0 ? p->kp.splits : 1;   /* "splits" of the tail tiles */
   if (smem) *smem = p->smem;
   return OK;
 }
