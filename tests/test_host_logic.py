@@ -117,6 +117,23 @@ def test_synthetic_imdb_and_tf_shim(tmp_path):
         sys.modules.pop("tensorflow", None)
 
 
+def test_result_file_formats(tmp_path):
+    """VOC text lines (+1 pixel shift, %.3f/%.1f) and COCO json (xywh with +1 extents), as the reference writes them."""
+    import json
+    from datasets.factory import SimpleImdb
+    imdb = SimpleImdb("fmt", ["/x/000012.jpg", "/x/000034.png"], 3)
+    e = np.zeros((0, 5), np.float32)
+    all_boxes = [[e, e], [np.array([[10.26, 20.0, 110.5, 220.04, 0.98765]], np.float32), e],
+                 [e, np.array([[0.0, 1.0, 2.0, 3.0, 0.5], [5.5, 6.5, 7.5, 8.5, 0.25]], np.float32)]]
+    files = imdb.write_voc_results(all_boxes, str(tmp_path))
+    assert open(files[0]).read() == "000012 0.988 11.3 21.0 111.5 221.0\n"
+    assert open(files[1]).read() == "000034 0.500 1.0 2.0 3.0 4.0\n000034 0.250 6.5 7.5 8.5 9.5\n"
+    res = imdb.write_coco_results(all_boxes, str(tmp_path / "r.json"))
+    assert json.load(open(tmp_path / "r.json")) == res and len(res) == 3
+    assert res[1] == {"image_id": "000034", "category_id": 2, "bbox": [0.0, 1.0, 3.0, 3.0], "score": 0.5}
+    assert imdb.evaluate_detections(all_boxes, str(tmp_path)) == [0, 1, 2]
+
+
 GLOO_WORKER = textwrap.dedent("""
     import os, sys
     sys.path.insert(0, %r)

@@ -19,7 +19,7 @@
 // lo planes into a 4-deep TMEM ring; tcgen05.mma runs in TS mode (A from TMEM, B from smem).
 // r01 finding 2: the tensor core adds into its fp32 accumulator with truncation (error grows linearly with the
 // number of MMA steps, ~2.4e-5 relative at K=3136), so accumulation is two-level: TMEM holds only the partial
-// sum of a short chunk of k-blocks (double buffered), which the epilogue warps add into fp32 REGISTER
+// sum of a short chunk of k-blocks, which the epilogue warps add into fp32 REGISTER
 // accumulators with round-to-nearest adds.  r01 finding 3: every such promotion stalls the tensor pipe for ~950
 // cycles (tcgen05.ld of a 128x128 fp32 tile vs the MMAs' own TMEM traffic; independent of warp placement and of
 // code shape), so the chunk length trades accuracy for speed (with all 12 MMAs of a k-block in one accumulator:

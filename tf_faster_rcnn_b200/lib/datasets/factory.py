@@ -28,12 +28,50 @@ class SimpleImdb(object):
     def competition_mode(self, on):
         pass
 
+    def image_id_at(self, i):
+        return os.path.splitext(os.path.basename(self._paths[i]))[0]
+
+    def write_voc_results(self, all_boxes, output_dir):
+        """Per-class `comp4_det_test_<cls>.txt` in the VOCdevkit format (lib/datasets/pascal_voc.py:203-219):
+        `<image id> <score %.3f> <x1+1 %.1f> <y1+1> <x2+1> <y2+1>` (the devkit is 1-based)."""
+        files = []
+        for j, cls in enumerate(self._classes):
+            if j == 0:
+                continue
+            path = os.path.join(output_dir, "comp4_det_test_%s.txt" % cls)
+            with open(path, "wt") as f:
+                for i in range(len(self._paths)):
+                    dets = all_boxes[j][i]
+                    for k in range(len(dets)):
+                        f.write("{:s} {:.3f} {:.1f} {:.1f} {:.1f} {:.1f}\n".format(
+                            self.image_id_at(i), dets[k][-1], dets[k][0] + 1, dets[k][1] + 1, dets[k][2] + 1, dets[k][3] + 1))
+            files.append(path)
+        return files
+
+    def write_coco_results(self, all_boxes, res_file):
+        """COCO results json (lib/datasets/coco.py:258-292): bbox = [x, y, w, h] with w = x2 - x1 + 1, h = y2 - y1 + 1."""
+        import json
+        results = []
+        for j in range(1, len(self._classes)):
+            for i in range(len(self._paths)):
+                dets = np.asarray(all_boxes[j][i], dtype=np.float64)
+                for k in range(len(dets)):
+                    x1, y1, x2, y2, sc = dets[k][:5]
+                    results.append({"image_id": self.image_id_at(i), "category_id": j,
+                                    "bbox": [float(x1), float(y1), float(x2 - x1 + 1), float(y2 - y1 + 1)], "score": float(sc)})
+        with open(res_file, "w") as f:
+            json.dump(results, f)
+        return results
+
     def evaluate_detections(self, all_boxes, output_dir=None):
-        """No ground truth exists for these sets: writes a per-class detection count summary instead of AP."""
+        """No ground truth exists for these sets: writes the VOC-format and COCO-format result files plus a per-class
+        detection count summary instead of computing AP."""
         counts = [int(sum(len(d) for d in per_image)) for per_image in all_boxes]
         if output_dir:
             with open(os.path.join(output_dir, "detection_counts.pkl"), "wb") as f:
                 pickle.dump(counts, f)
+            self.write_voc_results(all_boxes, output_dir)
+            self.write_coco_results(all_boxes, os.path.join(output_dir, "detections_%s_results.json" % self._name))
         print("detections per class:", counts[1:])
         return counts
 
