@@ -97,6 +97,10 @@ typedef struct {
 
 int frcnn_conv_plan_create(frcnn_conv_plan** out, const frcnn_conv_desc* d);
 int frcnn_conv_plan_run(const frcnn_conv_plan* p, void* stream);
+/* Host-only (no CUDA call): the work decomposition frcnn_conv_plan_create would choose on a GPU with sm_count SMs.  Device
+ * pointers in *d are ignored.  out16 = {block_n, tile_n, tile_h, tile_w, m_tiles, n_tiles, tiles, split_tiles, splits,
+ * k_blocks_per_split, work_units, grid, k_blocks, k_blocks_per_chunk, tiles_h, tiles_w}. */
+int frcnn_conv_plan_geometry(const frcnn_conv_desc* d, int sm_count, int* out16);
 int frcnn_conv_plan_info(const frcnn_conv_plan* p, int* block_n, int* tile_n, int* tile_h, int* tile_w,
                          int* grid_m, int* grid_n, int* splits, int* smem_bytes);
 /* debug aid: trace_dev (int64[64*8], device) receives clock64() stamps of the pipeline hand-offs of CTA (0,0)

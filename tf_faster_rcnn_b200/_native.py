@@ -36,6 +36,7 @@ SIGNATURES = {
     "frcnn_nms_sorted_dev": (ci, [vp, ci, cf, cu, ci, vp, vp, vp]),
     "frcnn_conv_plan_create": (ci, [C.POINTER(vp), C.POINTER(ConvDesc)]),
     "frcnn_conv_plan_run": (ci, [vp, vp]),
+    "frcnn_conv_plan_geometry": (ci, [C.POINTER(ConvDesc), ci, ip]),
     "frcnn_conv_plan_info": (ci, [vp, ip, ip, ip, ip, ip, ip, ip, ip]),
     "frcnn_conv_plan_set_trace": (ci, [vp, vp]),
     "frcnn_conv_plan_destroy": (None, [vp]),

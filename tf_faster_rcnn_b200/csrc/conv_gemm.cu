@@ -609,27 +609,33 @@ static int launch(const frcnn_conv_plan* p, cudaStream_t st) {
   return OK;
 }
 
-extern "C" int frcnn_conv_plan_create(frcnn_conv_plan** out, const frcnn_conv_desc* d) {
-  FRCNN_REQUIRE(out && d, "null argument");
+// Host-side work decomposition of one layer (no CUDA calls: unit-testable on a CPU box through frcnn_conv_plan_geometry).
+struct Geometry {
+  int n, h, w, ho, wo;           // after flattening 1x1/stride-1 layers to one row of n*h*w pixels
+  int tn, th, tw, tiles_w, tiles_h, tiles_n;
+  long m_tiles;
+  int num_kb, bn, n_tiles, kpc;
+  long tiles, n_tail;
+  int splits, kbs;
+  long total_units;
+  int grid;
+};
+
+static int decide_geometry(const frcnn_conv_desc* d, int sms, Geometry* g) {
   FRCNN_REQUIRE(d->cin > 0 && d->cin % BLOCK_K == 0, "cin=%d must be a positive multiple of 32", d->cin);
   FRCNN_REQUIRE(d->kh >= 1 && d->kw >= 1 && d->stride >= 1 && d->stride <= 8, "bad filter geometry");
-  FRCNN_REQUIRE(d->in_dev && d->w_hi_dev && d->w_lo_dev && d->out_dev, "null device pointer");
   FRCNN_REQUIRE(d->n > 0 && d->h > 0 && d->w > 0 && d->ho > 0 && d->wo > 0 && d->cout > 0, "bad shape");
-  frcnn_conv_plan* p = (frcnn_conv_plan*)aligned_alloc(64, (sizeof(frcnn_conv_plan) + 63) / 64 * 64);
-  if (!p) { set_error("out of host memory"); return ERR_ARG; }
-  memset(p, 0, sizeof(*p));
-
-  int n = d->n, h = d->h, w = d->w, ho = d->ho, wo = d->wo;
-  const bool pointwise = d->kh == 1 && d->kw == 1 && d->stride == 1 && d->pad_t == 0 && d->pad_l == 0 && ho == h && wo == w;
+  FRCNN_REQUIRE(sms > 0, "bad SM count");
+  g->n = d->n; g->h = d->h; g->w = d->w; g->ho = d->ho; g->wo = d->wo;
+  const bool pointwise = d->kh == 1 && d->kw == 1 && d->stride == 1 && d->pad_t == 0 && d->pad_l == 0 && g->ho == g->h && g->wo == g->w;
   if (pointwise) {  // flatten all pixels into one row of "width" n*h*w: perfect 128-row tiles
-    w = wo = n * h * w; n = 1; h = ho = 1;
+    g->w = g->wo = g->n * g->h * g->w; g->n = 1; g->h = g->ho = 1;
   }
-  int tn, th, tw;
-  choose_tile(n, ho, wo, d->stride, &tn, &th, &tw);
-  const int tiles_w = cdiv(wo, tw), tiles_h = cdiv(ho, th), tiles_n = cdiv(n, tn);
-  const long m_tiles = (long)tiles_w * tiles_h * tiles_n;
-  const int num_kb = d->kh * d->kw * d->cin / BLOCK_K;
-
+  choose_tile(g->n, g->ho, g->wo, d->stride, &g->tn, &g->th, &g->tw);
+  g->tiles_w = cdiv(g->wo, g->tw); g->tiles_h = cdiv(g->ho, g->th); g->tiles_n = cdiv(g->n, g->tn);
+  g->m_tiles = (long)g->tiles_w * g->tiles_h * g->tiles_n;
+  g->num_kb = d->kh * d->kw * d->cin / BLOCK_K;
+  g->kpc = d->kb_per_chunk > 0 ? d->kb_per_chunk : 8;
   int bn = d->block_n;
   if (bn == 0) {
     long best = -1;
@@ -637,21 +643,73 @@ extern "C" int frcnn_conv_plan_create(frcnn_conv_plan** out, const frcnn_conv_de
     for (int i = 0; i < 2; ++i) {
       const int c = cands[i];
       if (c > 64 && c / 2 >= d->cout) continue;        // tile mostly empty
-      const long ctas = m_tiles * cdiv(d->cout, c);
-      const long waves = (ctas + 147) / 148;
-      // measured (profiles/r01): a k-block costs ~1400 cycles whatever block_n is (SS-mode tcgen05.mma is bound by the
-      // 128-row A operand read for N <= 128), plus ~6000 cycles of prologue/drain per CTA => fewest waves wins, widest tile on ties
-      const long cost = waves * (num_kb * 1400L + 6000L);
+      const long ctas = g->m_tiles * cdiv(d->cout, c);
+      const long waves = (ctas + sms - 1) / sms;
+      // measured (profiles/r01): a k-block costs about the same whatever block_n is (the 128-row A operand dominates for
+      // N <= 128), plus a fixed per-unit cost => fewest rounds wins, widest tile on ties
+      const long cost = waves * (g->num_kb * 1400L + 6000L);
       if (best < 0 || cost < best) { best = cost; bn = c; }
     }
   }
   FRCNN_REQUIRE(bn == 64 || bn == 128, "block_n must be 64 or 128");
+  g->bn = bn;
+  g->n_tiles = cdiv(d->cout, bn);
+  g->tiles = g->m_tiles * g->n_tiles;
+  FRCNN_REQUIRE(g->tiles <= 0x3fffffffL, "too many tiles");
+  // ---- whole tiles + K-split tail (see ConvKernelParams) ---------------------------------------------------------------
+  long n_tail = 0; int splits = 1;
+  const int num_kb = g->num_kb;
+  const int max_split = num_kb / 8 < 8 ? num_kb / 8 : 8;        // >= 8 k-blocks (one chunk) per split, at most 8 splits
+  if (d->split_k > 1) {                                         // forced: every tile is split
+    n_tail = g->tiles; splits = d->split_k;
+  } else if (d->split_k == 0 && max_split >= 2) {
+    const long rem = g->tiles % sms;
+    // measured (r01): a split unit still pays ~7 us of per-unit overhead and the reduce pass ~10 us, so the ragged round is
+    // only worth splitting when the K loop is long (>= 48 k-blocks); small layers gain from 16 k-blocks on.
+    if (g->tiles <= sms / 2) { if (num_kb >= 16) { n_tail = g->tiles; splits = (int)(sms / g->tiles); } }   // layer too small to fill the GPU
+    else if (g->tiles > sms && rem > 0 && rem <= sms / 2 && num_kb >= 48) { n_tail = rem; splits = (int)(sms / rem); }   // ragged last round
+    if (splits > max_split) splits = max_split;
+    if (splits < 2) { n_tail = 0; splits = 1; }
+  }
+  int kbs = cdiv(num_kb, splits);                              // (a unit's last chunk may be shorter than kb_per_chunk)
+  splits = cdiv(num_kb, kbs);
+  if (splits < 2) { n_tail = 0; splits = 1; }
+  FRCNN_REQUIRE(splits <= 64, "bad split_k");
+  g->n_tail = n_tail; g->splits = splits; g->kbs = kbs;
+  g->total_units = (g->tiles - n_tail) + n_tail * splits;
+  FRCNN_REQUIRE(g->total_units <= 0x7fffffffL, "too many work units");
+  g->grid = (int)(g->total_units < sms ? g->total_units : sms);   // persistent: one CTA per SM walks the units
+  return OK;
+}
 
+extern "C" int frcnn_conv_plan_geometry(const frcnn_conv_desc* d, int sm_count, int* out16) {
+  FRCNN_REQUIRE(d && out16, "null argument");
+  Geometry g;
+  int rc = decide_geometry(d, sm_count, &g);
+  if (rc) return rc;
+  const int v[16] = {g.bn, g.tn, g.th, g.tw, (int)g.m_tiles, g.n_tiles, (int)g.tiles, (int)g.n_tail, g.splits, g.kbs,
+                     (int)g.total_units, g.grid, g.num_kb, g.kpc, g.tiles_h, g.tiles_w};
+  for (int i = 0; i < 16; ++i) out16[i] = v[i];
+  return OK;
+}
+
+extern "C" int frcnn_conv_plan_create(frcnn_conv_plan** out, const frcnn_conv_desc* d) {
+  FRCNN_REQUIRE(out && d, "null argument");
+  FRCNN_REQUIRE(d->in_dev && d->w_hi_dev && d->w_lo_dev && d->out_dev, "null device pointer");
+  int sms = 148;
+  { int dev = 0; cudaDeviceProp pr; if (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&pr, dev) == cudaSuccess && pr.multiProcessorCount > 0) sms = pr.multiProcessorCount; }
+  Geometry g;
+  int grc = decide_geometry(d, sms, &g);
+  if (grc) return grc;
+  frcnn_conv_plan* p = (frcnn_conv_plan*)aligned_alloc(64, (sizeof(frcnn_conv_plan) + 63) / 64 * 64);
+  if (!p) { set_error("out of host memory"); return ERR_ARG; }
+  memset(p, 0, sizeof(*p));
+  const int bn = g.bn;
   // A: NHWC activations as a rank-4 tensor {C, W, H, N}; traversal stride = conv stride on W and H
   {
-    uint64_t dims[4] = {(uint64_t)d->cin, (uint64_t)w, (uint64_t)h, (uint64_t)n};
-    uint64_t strides[3] = {(uint64_t)d->cin * 4, (uint64_t)w * d->cin * 4, (uint64_t)h * w * d->cin * 4};
-    uint32_t box[4] = {(uint32_t)BLOCK_K, (uint32_t)(tw * d->stride), (uint32_t)(th * d->stride), (uint32_t)tn};
+    uint64_t dims[4] = {(uint64_t)d->cin, (uint64_t)g.w, (uint64_t)g.h, (uint64_t)g.n};
+    uint64_t strides[3] = {(uint64_t)d->cin * 4, (uint64_t)g.w * d->cin * 4, (uint64_t)g.h * g.w * d->cin * 4};
+    uint32_t box[4] = {(uint32_t)BLOCK_K, (uint32_t)(g.tw * d->stride), (uint32_t)(g.th * d->stride), (uint32_t)g.tn};
     uint32_t es[4] = {1, (uint32_t)d->stride, (uint32_t)d->stride, 1};
     int rc = encode_map(&p->tmA, d->in_dev, 4, dims, strides, box, es);
     if (rc) { free(p); return rc; }
@@ -668,47 +726,23 @@ extern "C" int frcnn_conv_plan_create(frcnn_conv_plan** out, const frcnn_conv_de
   }
   ConvKernelParams& k = p->kp;
   k.out = d->out_dev; k.residual = d->residual_dev; k.scale = d->scale_dev; k.shift = d->shift_dev;
-  k.cout = d->cout; k.ho = ho; k.wo = wo; k.nimg = n;
-  k.tn = tn; k.th = th; k.tw = tw; k.tiles_h = tiles_h; k.tiles_w = tiles_w;
+  k.cout = d->cout; k.ho = g.ho; k.wo = g.wo; k.nimg = g.n;
+  k.tn = g.tn; k.th = g.th; k.tw = g.tw; k.tiles_h = g.tiles_h; k.tiles_w = g.tiles_w;
   k.kh = d->kh; k.kw = d->kw; k.cin = d->cin; k.stride = d->stride; k.pad_t = d->pad_t; k.pad_l = d->pad_l;
   k.act = d->act;
-  k.a_box_bytes = tn * th * tw * BLOCK_K * 4;
-  k.kb_per_chunk = d->kb_per_chunk > 0 ? d->kb_per_chunk : 8;
+  k.a_box_bytes = g.tn * g.th * g.tw * BLOCK_K * 4;
+  k.kb_per_chunk = g.kpc;
   k.trace = nullptr;
-  // ---- work decomposition: whole tiles + K-split tail (see ConvKernelParams) ------------------------------------------
-  int sms = 148;
-  { int dev = 0; cudaDeviceProp pr; if (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&pr, dev) == cudaSuccess && pr.multiProcessorCount > 0) sms = pr.multiProcessorCount; }
-  k.m_tiles = (int)m_tiles; k.n_tiles = cdiv(d->cout, bn);
-  const long tiles = m_tiles * k.n_tiles;
-  FRCNN_REQUIRE(tiles <= 0x3fffffffL, "too many tiles");
-  long n_tail = 0; int splits = 1;
-  const int max_split = num_kb / 8 < 8 ? num_kb / 8 : 8;        // >= 8 k-blocks (one chunk) per split, at most 8 splits
-  if (d->split_k > 1) {                                         // forced: every tile is split
-    n_tail = tiles; splits = d->split_k;
-  } else if (d->split_k == 0 && max_split >= 2) {
-    const long rem = tiles % sms;
-    // measured (r01): a split unit still pays ~7 us of per-unit overhead and the reduce pass ~10 us, so the ragged round is
-    // only worth splitting when the K loop is long (>= 48 k-blocks); small layers gain from 16 k-blocks on.
-    if (tiles <= sms / 2) { if (num_kb >= 16) { n_tail = tiles; splits = (int)(sms / tiles); } }  // layer too small to fill the GPU
-    else if (tiles > sms && rem > 0 && rem <= sms / 2 && num_kb >= 48) { n_tail = rem; splits = (int)(sms / rem); }   // ragged last round
-    if (splits > max_split) splits = max_split;
-    if (splits < 2) { n_tail = 0; splits = 1; }
-  }
-  int kbs = cdiv(num_kb, splits);
-  kbs = cdiv(kbs, k.kb_per_chunk) * k.kb_per_chunk;            // whole chunks per split
-  splits = cdiv(num_kb, kbs);
-  if (splits < 2) { n_tail = 0; splits = 1; }
-  k.kb_per_split = kbs; k.splits = splits; k.n_full = (int)(tiles - n_tail);
-  const long total_units = (tiles - n_tail) + n_tail * splits;
-  FRCNN_REQUIRE(total_units <= 0x7fffffffL, "too many work units");
-  k.total_units = (int)total_units;
-  k.ws = nullptr; p->ws = nullptr; p->n_tail = (int)n_tail;
-  if (n_tail > 0) {
-    cudaError_t e = cudaMalloc(&p->ws, (size_t)n_tail * splits * BLOCK_M * bn * sizeof(float));
+  k.m_tiles = (int)g.m_tiles; k.n_tiles = g.n_tiles;
+  k.kb_per_split = g.kbs; k.splits = g.splits; k.n_full = (int)(g.tiles - g.n_tail);
+  k.total_units = (int)g.total_units;
+  k.ws = nullptr; p->ws = nullptr; p->n_tail = (int)g.n_tail;
+  if (g.n_tail > 0) {
+    cudaError_t e = cudaMalloc(&p->ws, (size_t)g.n_tail * g.splits * BLOCK_M * bn * sizeof(float));
     if (e != cudaSuccess) { free(p); return cuda_fail(e, "split-tile workspace", __FILE__, __LINE__); }
     k.ws = p->ws;
   }
-  p->grid = dim3((unsigned)(total_units < sms ? total_units : sms), 1, 1);   // persistent: one CTA per SM walks the units
+  p->grid = dim3((unsigned)g.grid, 1, 1);
   p->block_n = bn;
   p->stages = RING;
   p->smem = bn == 128 ? smem_bytes<128>() : smem_bytes<64>();
