@@ -151,6 +151,13 @@ __device__ __forceinline__ float ld_nc_f32_pinned(const float* p) {
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// same rounding (nearest, ties away from zero) for finite inputs in two integer ops: add half a tf32 ulp to the magnitude
+// bits, clear the low 13 bits.  cvt.rna.tf32 additionally special-cases Inf/NaN (an extra compare + select per element),
+// which the operand splitter -- it shares its scheduler with the MMA-issuing warp -- does not need.
+__device__ __forceinline__ float to_tf32_fast(float x) {
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+}
+
 // round-to-nearest fp32 -> tf32 (result is an fp32 bit pattern with the low 13 mantissa bits clear)
 __device__ __forceinline__ float to_tf32(float x) {
   uint32_t r;

@@ -275,11 +275,11 @@ conv_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           const float4 v = *reinterpret_cast<const float4*>(arow + ((c ^ (row & 7)) << 4));
-          const float h0 = to_tf32(v.x), h1 = to_tf32(v.y), h2 = to_tf32(v.z), h3 = to_tf32(v.w);
+          const float h0 = to_tf32_fast(v.x), h1 = to_tf32_fast(v.y), h2 = to_tf32_fast(v.z), h3 = to_tf32_fast(v.w);
           hi[4 * c + 0] = __float_as_uint(h0); hi[4 * c + 1] = __float_as_uint(h1);
           hi[4 * c + 2] = __float_as_uint(h2); hi[4 * c + 3] = __float_as_uint(h3);
-          lo[4 * c + 0] = __float_as_uint(to_tf32(__fsub_rn(v.x, h0))); lo[4 * c + 1] = __float_as_uint(to_tf32(__fsub_rn(v.y, h1)));
-          lo[4 * c + 2] = __float_as_uint(to_tf32(__fsub_rn(v.z, h2))); lo[4 * c + 3] = __float_as_uint(to_tf32(__fsub_rn(v.w, h3)));
+          lo[4 * c + 0] = __float_as_uint(to_tf32_fast(__fsub_rn(v.x, h0))); lo[4 * c + 1] = __float_as_uint(to_tf32_fast(__fsub_rn(v.y, h1)));
+          lo[4 * c + 2] = __float_as_uint(to_tf32_fast(__fsub_rn(v.z, h2))); lo[4 * c + 3] = __float_as_uint(to_tf32_fast(__fsub_rn(v.w, h3)));
         }
         mbar_arrive(&a_empty[slot]);                          // raw tile consumed (values are in registers)
         mbar_wait(&mma_done[slot], par ^ 1u);                  // TMEM A slot no longer read by the tensor core
