@@ -1,0 +1,1 @@
+"""B200-native Faster R-CNN inference path (package root; see README.md / DESIGN.md)."""

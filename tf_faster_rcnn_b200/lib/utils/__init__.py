@@ -1,0 +1,1 @@
+"""Mirror of the reference's lib/utils import surface for the B200 path (tf_faster_rcnn_b200/lib)."""
