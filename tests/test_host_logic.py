@@ -76,6 +76,17 @@ def test_image_blob_scaling_rule_matches_oracle():
         assert max(blob.shape[1:3]) <= 1000 + 1
 
 
+def test_blob_geometry_predicts_opencv_output_size():
+    """blob_geometry (used by the device preprocess path) == the size cv2.resize(fx, fy) actually produces."""
+    from model.test import _get_image_blob, blob_geometry
+    rng = np.random.default_rng(1)
+    for _ in range(40):
+        h, w = int(rng.integers(120, 1400)), int(rng.integers(120, 1400))
+        blob, scales = _get_image_blob(np.zeros((h, w, 3), np.uint8))
+        H, W, f = blob_geometry((h, w, 3))
+        assert (H, W) == blob.shape[1:3] and f == scales[0], (h, w)
+
+
 def test_nms_threshold_rule_and_empty_input():
     from tf_faster_rcnn_b200 import engine, _native as N
     from model.nms_wrapper import nms
