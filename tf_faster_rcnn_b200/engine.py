@@ -72,6 +72,7 @@ class Tape:
         self.flops = 0.0       # algorithmic 2*MAC of every conv/FC layer recorded
         self.conv_flops = 0.0  # ... of the tcgen05 implicit-GEMM launches only
         self.bufs = []
+        self.conv_plans = []   # ops.ConvPlan objects, in launch order
 
     def new(self, *shape, dtype=torch.float32):
         t = torch.empty(shape, dtype=dtype, device="cuda")
@@ -92,6 +93,7 @@ class Tape:
         ho, wo, pt, pl = ops.conv_out_hw(h, w, pc.kh, stride, mode)
         out = self.new(n, ho, wo, pc.cout)
         plan = ops.ConvPlan(x, pc, out, stride, pt, pl, act, residual)
+        self.conv_plans.append(plan)
         self.add("conv:" + name, plan.run)
         fl = 2.0 * n * ho * wo * pc.cout * pc.kh * pc.kw * pc.cin
         self.flops += fl
