@@ -1,9 +1,7 @@
 """Minimal stand-in for the handful of TensorFlow-1.x symbols the reference's tools touch
 (tools/demo.py:24,129-144; tools/test_net.py:18,86-117) so that they can drive this engine unchanged.
 Only used when a real `tensorflow` is not importable (tf_faster_rcnn_b200.paths.add_lib_path(with_shims=True)).
-No graph, no ops: the Session is an opaque token; Saver.restore loads an .npz of TF-named variables."""
-import os
-import numpy as np
+No graph, no ops: the Session is an opaque token; Saver.restore reads a TF V2 checkpoint (or an .npz) of TF-named variables."""
 
 __version__ = "1.x-shim (tf_faster_rcnn_b200)"
 
@@ -59,13 +57,10 @@ class Session(object):
 
 class _Saver(object):
     def restore(self, sess, save_path):
-        """Loads `<save_path>.npz` (or save_path itself if it is an .npz): TF variable name -> array."""
-        path = save_path if save_path.endswith(".npz") else save_path + ".npz"
-        if not os.path.isfile(path):
-            raise IOError("no weights at %s: TF bundle (.index/.data) reading is not implemented; export variables "
-                          "to an .npz keyed by TF variable names (tools/make_synthetic_ckpt.py writes one)" % path)
-        with np.load(path) as z:
-            tensors = {k: z[k] for k in z.files}
+        """Assigns every variable found under `save_path`: a TensorFlow V2 checkpoint (`.index` + `.data-*`, read by
+        tf_faster_rcnn_b200.checkpoint without TensorFlow) or, failing that, `<save_path>.npz` keyed by TF names."""
+        from tf_faster_rcnn_b200 import checkpoint
+        tensors = checkpoint.load_variables(save_path)
         for net in _networks():
             net.load_weights(tensors)
 

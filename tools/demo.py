@@ -17,7 +17,7 @@ from utils.timer import Timer
 from nets.vgg16 import vgg16
 from nets.resnet_v1 import resnetv1
 from nets.mobilenet_v1 import mobilenetv1
-from tf_faster_rcnn_b200 import synth
+from tf_faster_rcnn_b200 import checkpoint, synth
 
 
 def build(net_name, num_classes, model=None):
@@ -25,8 +25,7 @@ def build(net_name, num_classes, model=None):
     net = vgg16() if net_name == "vgg16" else mobilenetv1() if net_name == "mobile" else resnetv1(int(net_name[3:]))
     net.create_architecture("TEST", num_classes, tag="default", anchor_scales=cfg.ANCHOR_SCALES, anchor_ratios=cfg.ANCHOR_RATIOS)
     if model:
-        with np.load(model if model.endswith(".npz") else model + ".npz") as z:
-            net.load_weights({k: z[k] for k in z.files})
+        net.load_weights(checkpoint.load_variables(model))          # TF V2 bundle or .npz
     else:
         net.load_weights(synth.make(net_name, num_classes, net.num_anchors))
     return net
