@@ -1,6 +1,7 @@
-"""`get_imdb(name)` (lib/datasets/factory.py:50-54).  The VOC/COCO loaders need datasets that are not available
-offline and are out of scope; this build registers image-directory and synthetic imdbs that satisfy exactly what
-test_net needs (lib/model/test.py:138-192): name, num_classes, image_index, image_path_at, evaluate_detections."""
+"""`get_imdb(name)` / `list_imdbs()` (lib/datasets/factory.py:17-52): the reference's names -- voc_{2007,2012}_{train,val,
+trainval,test}[_diff], coco_2014_{train,val,minival,valminusminival,trainval}, coco_2015_{test,test-dev} -- resolve to
+datasets.pascal_voc / datasets.coco (constructed lazily: they need the data on disk), plus image-directory and synthetic
+imdbs that satisfy exactly what test_net needs (lib/model/test.py:138-192) when no dataset is available."""
 import os
 import pickle
 import tempfile
@@ -89,8 +90,28 @@ def _synthetic(n, num_classes, h=375, w=500, seed=3):
     return SimpleImdb("synthetic_%d_%d" % (n, num_classes), paths, num_classes)
 
 
+def _voc(split, year, use_diff=False):
+    from datasets.pascal_voc import pascal_voc
+    return pascal_voc(split, year, use_diff=use_diff)
+
+
+def _coco(split, year):
+    from datasets.coco import coco
+    return coco(split, year)
+
+
+for _year in ("2007", "2012"):
+    for _split in ("train", "val", "trainval", "test"):
+        _SETS["voc_{}_{}".format(_year, _split)] = (lambda split=_split, year=_year: _voc(split, year))
+        _SETS["voc_{}_{}_diff".format(_year, _split)] = (lambda split=_split, year=_year: _voc(split, year, True))
+for _split in ("train", "val", "minival", "valminusminival", "trainval"):
+    _SETS["coco_2014_{}".format(_split)] = (lambda split=_split: _coco(split, "2014"))
+for _split in ("test", "test-dev"):
+    _SETS["coco_2015_{}".format(_split)] = (lambda split=_split: _coco(split, "2015"))
+
+
 def get_imdb(name):
-    """'synthetic_<n>_<classes>' | 'dir:<path>:<classes>' | a name registered with register()."""
+    """A registered name (reference sets above, register()) | 'synthetic_<n>_<classes>' | 'dir:<path>:<classes>'."""
     if name in _SETS:
         return _SETS[name]()
     if name.startswith("synthetic_"):
