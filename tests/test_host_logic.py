@@ -111,7 +111,7 @@ def test_synthetic_imdb_and_tf_shim(tmp_path):
     imdb = get_imdb("synthetic_3_5")
     assert imdb.num_classes == 5 and len(imdb.image_index) == 3 and os.path.isfile(imdb.image_path_at(2))
     with pytest.raises(KeyError):
-        get_imdb("voc_2007_test")
+        get_imdb("imagenet_2012_val")
     from tf_faster_rcnn_b200 import paths
     sys.path.append(paths.SHIMS)
     try:
