@@ -189,6 +189,65 @@ def test_two_rank_record_gather_over_gloo(tmp_path):
     assert all("ok" in o for o in outs)
 
 
+SHARDED_WORKER = textwrap.dedent("""
+    import os, sys, pickle
+    sys.path.insert(0, %r)
+    import numpy as np, torch, torch.distributed as dist
+    from tf_faster_rcnn_b200 import paths
+    paths.add_lib_path()
+    from model import test as T
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+
+    class Imdb:
+        num_classes = 4
+        def __init__(self, n): self.image_index = list(range(n))
+
+    def fake(i, cap=12):            # a deterministic stand-in for the device path: records depend on the image only
+        n = (i * 5) %% 7
+        det = torch.zeros(cap, 6)
+        for k in range(n):
+            det[k] = torch.tensor([i, k, i + 20, k + 20, 1.0 - 0.1 * k, 1 + (i + k) %% 3], dtype=torch.float32)
+        return det, torch.tensor([n], dtype=torch.int32)
+
+    out = {}
+    for n_images in (5, 1, 0, 4):
+        calls = []
+        boxes = T._test_net_sharded(Imdb(n_images), lambda i: (calls.append(i), fake(i))[1], verbose=False)
+        assert calls == list(range(rank, n_images, world)), calls           # each rank ran only its shard
+        out[n_images] = boxes
+    if rank == 0:
+        with open(os.environ["OUT"], "wb") as f:
+            pickle.dump(out, f)
+    dist.barrier()
+    dist.destroy_process_group()
+    print("rank", rank, "ok")
+""")
+
+
+def test_sharded_test_net_matches_single_process(tmp_path):
+    """model.test._test_net_sharded over 2 gloo ranks (5 / 1 / 0 / 4 images: ragged last step, an idle rank, empty set)
+    assembles the same all_boxes on every rank as a single-process pass over the same per-image records."""
+    import pickle
+    script = tmp_path / "s.py"
+    script.write_text(SHARDED_WORKER % ROOT)
+    out = str(tmp_path / "boxes.pkl")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29613", WORLD_SIZE="2", OUT=out)
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r)), stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+             for r in range(2)]
+    outs = [p.communicate(timeout=240)[0].decode() for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    got = pickle.load(open(out, "rb"))
+    for n_images, boxes in got.items():
+        assert len(boxes) == 4 and all(len(per_image) == n_images for per_image in boxes)
+        for i in range(n_images):
+            n = (i * 5) % 7
+            rows = np.array([[i, k, i + 20, k + 20, np.float32(1.0 - 0.1 * k), 1 + (i + k) % 3] for k in range(n)], np.float32).reshape(-1, 6)
+            for j in range(1, 4):
+                want = rows[rows[:, 5] == j, :5]
+                assert np.array_equal(np.asarray(boxes[j][i], np.float32).reshape(-1, 5), want), (n_images, i, j)
+
+
 @pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree only exists in the authoring container")
 def test_reference_demo_script_drives_this_lib_unchanged(tmp_path):
     """Runs the reference's OWN tools/demo.py (unmodified, in place) against this repo's lib/ + shims.  Without a GPU it

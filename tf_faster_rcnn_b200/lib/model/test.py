@@ -4,7 +4,11 @@ im_detect :86-107, apply_nms :109-136, test_net :138-192.
 im_detect keeps the reference data flow (host blob -> net.test_image -> decode -> clip) but the decode/clip
 run in a device kernel right behind the CUDA graph (frcnn_bbox_decode) instead of NumPy.  test_net by default
 also keeps the per-class NMS + max_per_image cap on the device (frcnn_detect_post); setting
-`FUSED_POST = False` runs the reference's Python loop over `nms()` instead (same results)."""
+`FUSED_POST = False` runs the reference's Python loop over `nms()` instead (same results).
+
+Under torchrun (torch.distributed initialised, world size W > 1) test_net shards the imdb -- image i on rank i mod W --
+and all-gathers each step's fixed-size detection records straight from the buffers the last kernel wrote
+(tf_faster_rcnn_b200/parallel.py); rank 0 assembles all_boxes, writes detections.pkl and evaluates."""
 import os
 import pickle
 
@@ -134,12 +138,67 @@ def detect_image(net, im, thresh=0., max_per_image=100):
     return [det[cls == j, :5] for j in range(C)]
 
 
+def _detect_records(net, im, thresh, max_per_image):
+    """Fused path for one image, results left on the device: (det [max_det,6] fp32, ndet [1] int32), stream-ordered."""
+    blobs, im_scales = _get_blobs(im)
+    blob = blobs['data']
+    im_info = np.array([blob.shape[1], blob.shape[2], im_scales[0]], dtype=np.float32)
+    net.options["score_thresh"], net.options["max_per_image"] = float(thresh), int(max_per_image)
+    net.options["nms_thresh"] = cfg.TEST.NMS
+    plan = net._run(blob, im_info, post=True, detect=True, orig_hw=im.shape[:2])
+    return plan.det, plan.ndet
+
+
+def _test_net_sharded(imdb, detect_records, verbose=True):
+    """Lock-step loop over ceil(N / W) steps; every rank returns the complete all_boxes[cls][image].
+    detect_records(image index) -> (det [max_det,6] float tensor, ndet [1] int32 tensor) on the collective's device."""
+    import torch.distributed as dist
+    from tf_faster_rcnn_b200 import parallel
+    rank, world = dist.get_rank(), dist.get_world_size()
+    num_images = len(imdb.image_index)
+    all_boxes = [[[] for _ in range(num_images)] for _ in range(imdb.num_classes)]
+    mine = parallel.shard_indices(num_images, rank, world)
+    device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    gather = idle = None
+    timer = Timer()
+    for step in range(parallel.steps_for(num_images, world)):
+        timer.tic()
+        rec = detect_records(mine[step]) if step < len(mine) else None
+        if gather is None:
+            # ranks without an image (N < W) learn the record capacity from the others: one extra tiny collective, once
+            cap = torch.tensor([rec[0].shape[0] if rec is not None else 0], dtype=torch.int64, device=device)
+            dist.all_reduce(cap, op=dist.ReduceOp.MAX)
+            idle = (torch.zeros(int(cap.item()), 6, dtype=torch.float32, device=device),
+                    torch.zeros(1, dtype=torch.int32, device=device))
+            gather = parallel.RecordGather(idle[0], idle[1], world)
+        det, ndet = rec if rec is not None else idle
+        det_list, n_list = gather.gather(det, ndet)
+        parallel.records_to_all_boxes(all_boxes, step, world, det_list, n_list, num_images)
+        timer.toc()
+        if verbose and rank == 0:
+            print('im_detect: {:d}/{:d} {:.3f}s per step of {:d} images'.format(
+                min((step + 1) * world, num_images), num_images, timer.average_time, world))
+    return all_boxes
+
+
 def test_net(sess, net, imdb, weights_filename, max_per_image=100, thresh=0.):
     """Run the detector over imdb; all_boxes[cls][image] = [k,5]; pickles detections.pkl and evaluates."""
     np.random.seed(cfg.RNG_SEED)
     num_images = len(imdb.image_index)
-    all_boxes = [[[] for _ in range(num_images)] for _ in range(imdb.num_classes)]
     output_dir = get_output_dir(imdb, weights_filename)
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        assert FUSED_POST and cfg.TEST.BBOX_REG, "sharded test_net gathers the fused path's device records"
+        all_boxes = _test_net_sharded(
+            imdb, lambda i: _detect_records(net, cv2.imread(imdb.image_path_at(i)), thresh, max_per_image))
+        if dist.get_rank() == 0:
+            with open(os.path.join(output_dir, 'detections.pkl'), 'wb') as f:
+                pickle.dump(all_boxes, f, pickle.HIGHEST_PROTOCOL)
+            print('Evaluating detections')
+            imdb.evaluate_detections(all_boxes, output_dir)
+        dist.barrier()
+        return all_boxes
+    all_boxes = [[[] for _ in range(num_images)] for _ in range(imdb.num_classes)]
     _t = {'im_detect': Timer(), 'misc': Timer()}
     for i in range(num_images):
         im = cv2.imread(imdb.image_path_at(i))

@@ -1,7 +1,9 @@
 #!/usr/bin/env python
 """Run the detector over an imdb (counterpart of the reference's tools/test_net.py:58-122; same flags).
 
-    python tools/test_net.py --imdb synthetic_8_21 --net res101 [--cfg x.yml] [--model ckpt] [--set K V ...]"""
+    python tools/test_net.py --imdb synthetic_8_21 --net res101 [--cfg x.yml] [--model ckpt] [--set K V ...]
+    torchrun --nproc-per-node 8 --master-addr 127.0.0.1 tools/test_net.py --imdb voc_2007_test --net res101 --model ckpt
+        (one process per GPU: images are sharded i mod W, records all-gathered per step, rank 0 evaluates)"""
 import argparse
 import os
 import pprint
@@ -29,13 +31,26 @@ def parse_args():
     return p.parse_args()
 
 
+def init_distributed():
+    """One process per GPU when launched by torchrun (WORLD_SIZE > 1); a plain launch stays single-process."""
+    if int(os.environ.get("WORLD_SIZE", "1")) <= 1:
+        return 0
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    dist.init_process_group("nccl")
+    return dist.get_rank()
+
+
 if __name__ == '__main__':
     args = parse_args()
+    rank = init_distributed()
     if args.cfg_file is not None:
         cfg_from_file(args.cfg_file)
     if args.set_cfgs is not None:
         cfg_from_list(args.set_cfgs)
-    pprint.pprint({k: cfg[k] for k in ("TEST", "ANCHOR_SCALES", "ANCHOR_RATIOS", "USE_GPU_NMS", "USE_E2E_TF")})
+    if rank == 0:
+        pprint.pprint({k: cfg[k] for k in ("TEST", "ANCHOR_SCALES", "ANCHOR_RATIOS", "USE_GPU_NMS", "USE_E2E_TF")})
     filename = os.path.splitext(os.path.basename(args.model))[0] if args.model else 'default'
     tag = args.tag if args.tag else 'default'
     imdb = get_imdb(args.imdb_name)
