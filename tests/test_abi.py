@@ -52,3 +52,24 @@ def test_conv_desc_struct_matches_header():
         decl = re.sub(r"^(const\s+)?(float\*|int)\s*", "", decl)
         fields += [f.strip().lstrip("*") for f in decl.split(",")]
     assert fields == [f[0] for f in _native.ConvDesc._fields_]
+
+
+def test_every_entry_rejects_null_arguments_before_touching_a_device():
+    """All-null / all-zero arguments: each status-returning entry answers ERR_ARG (-2) with a message -- it validates
+    before any CUDA call, so this runs (and must not crash) on a machine without a GPU."""
+    from tf_faster_rcnn_b200 import _native
+    L = _native.lib()
+    skip = {"frcnn_version", "frcnn_last_error", "frcnn_check_device", "frcnn_sort_workspace_bytes", "frcnn_conv_plan_destroy"}
+    checked = 0
+    for name in _native.SIGNATURES:
+        if name in skip:
+            continue
+        fn = getattr(L, name)
+        args = [None if t is ctypes.c_void_p else t() for t in fn.argtypes]
+        rc = fn(*args)
+        assert rc == -2, (name, rc)
+        assert _native.last_error(), name
+        checked += 1
+    assert checked >= 18
+    assert L.frcnn_sort_workspace_bytes(0) >= 0
+    L.frcnn_conv_plan_destroy(None)                       # destroying nothing is a no-op
