@@ -73,3 +73,16 @@ def test_every_entry_rejects_null_arguments_before_touching_a_device():
     assert checked >= 18
     assert L.frcnn_sort_workspace_bytes(0) >= 0
     L.frcnn_conv_plan_destroy(None)                       # destroying nothing is a no-op
+
+
+def test_product_package_never_imports_the_oracle():
+    """oracle/ is test infrastructure: only tests/, __graft_entry__.smoke() and bench.py's CPU arms may import it."""
+    offenders = []
+    for base in ("tf_faster_rcnn_b200", "tools"):
+        for d, _, files in os.walk(os.path.join(ROOT, base)):
+            for f in files:
+                if f.endswith(".py"):
+                    src = open(os.path.join(d, f)).read()
+                    if re.search(r"^\s*(from\s+oracle\b|import\s+oracle\b)", src, flags=re.M):
+                        offenders.append(os.path.join(d, f))
+    assert offenders == []
