@@ -141,3 +141,14 @@ def test_saver_restore_reads_bundle(tmp_path):
         assert net.weights is not None
     finally:
         network._REGISTRY[:] = before
+
+
+def test_command_line_list_and_conversions(tmp_path, capsys):
+    prefix = str(tmp_path / "a.ckpt")
+    ck.write_bundle(prefix, {"x/w": np.arange(6, dtype=np.float32).reshape(2, 3), "step": np.int64(3)})
+    ck._main(["list", prefix])
+    text = capsys.readouterr().out
+    assert "x/w" in text and "float32" in text and "[2, 3]" in text and "int64" in text
+    ck._main(["to-npz", prefix, str(tmp_path / "a.npz")])
+    ck._main(["to-bundle", str(tmp_path / "a.npz"), str(tmp_path / "b.ckpt")])
+    assert open(prefix + ".index", "rb").read() == open(str(tmp_path / "b.ckpt.index"), "rb").read()

@@ -463,3 +463,29 @@ def write_bundle(prefix, tensors, block_size=4096):
     out += footer + b"\x00" * (40 - len(footer)) + struct.pack("<Q", TABLE_MAGIC)
     with open(prefix + ".index", "wb") as f:
         f.write(bytes(out))
+
+
+def _main(argv=None):
+    """python -m tf_faster_rcnn_b200.checkpoint list <prefix> | to-npz <prefix> <out.npz> | to-bundle <in.npz> <prefix>"""
+    import argparse
+    ap = argparse.ArgumentParser(description=_main.__doc__)
+    ap.add_argument("command", choices=("list", "to-npz", "to-bundle"))
+    ap.add_argument("src")
+    ap.add_argument("dst", nargs="?")
+    ap.add_argument("--no-verify", action="store_true", help="skip CRC-32C verification")
+    a = ap.parse_args(argv)
+    if a.command == "list":
+        for name, code, shape in list_variables(a.src, verify=not a.no_verify):
+            print("%-72s %-8s %s" % (name, np.dtype(_DTYPES[code]).name if code in _DTYPES else "dtype%d" % code, list(shape)))
+    elif a.command == "to-npz":
+        skipped = []
+        np.savez(a.dst, **read_bundle(a.src, verify=not a.no_verify, skipped=skipped))
+        for name, why in skipped:
+            print("skipped %s (%s)" % (name, why))
+    else:
+        with np.load(a.src) as z:
+            write_bundle(a.dst, {k: z[k] for k in z.files})
+
+
+if __name__ == "__main__":
+    _main()
