@@ -152,3 +152,38 @@ def test_command_line_list_and_conversions(tmp_path, capsys):
     ck._main(["to-npz", prefix, str(tmp_path / "a.npz")])
     ck._main(["to-bundle", str(tmp_path / "a.npz"), str(tmp_path / "b.ckpt")])
     assert open(prefix + ".index", "rb").read() == open(str(tmp_path / "b.ckpt.index"), "rb").read()
+
+
+def test_spec_matches_generated_variables_and_restore_is_strict(tmp_path):
+    for net, C, A in (("vgg16", 21, 9), ("res50", 5, 9), ("mobile", 81, 12)):
+        w = synth.make(net, C, A)
+        sp = synth.spec(net, C, A)
+        assert list(w) == list(sp) and all(w[k].shape == tuple(sp[k]) for k in w)
+        assert synth.check(net, w, C, A) == []
+        assert synth.check(net, dict(w, **{"global_step": np.int64(1), "x/Momentum": np.zeros(3)}), C, A) == []   # extras ignored
+    assert synth.spec("mobile", 21, 9, depth_multiplier=0.5)["MobilenetV1/Conv2d_0/weights"] == (3, 3, 3, 16)
+    assert synth.spec("res50", 21, 9, rpn_channels=256)["resnet_v1_50/rpn_conv/3x3/weights"] == (3, 3, 1024, 256)
+
+    from tf_faster_rcnn_b200 import paths
+    paths.add_lib_path(with_shims=True)
+    import tensorflow as tf
+    from nets import network
+    from nets.resnet_v1 import resnetv1
+    before = list(network._REGISTRY)
+    try:
+        net = resnetv1(num_layers=50)
+        net.create_architecture("TEST", 21, tag="default", anchor_scales=[8, 16, 32])
+        assert net.arch_name() == "res50"
+        w = synth.make("res50", 5, 9)                     # a 5-class checkpoint into a 21-class graph
+        prefix = str(tmp_path / "five.ckpt")
+        ck.write_bundle(prefix, w)
+        with pytest.raises(ValueError, match="cls_score/weights: checkpoint has shape"):
+            tf.train.Saver().restore(tf.Session(), prefix)
+        del w["resnet_v1_50/block2/unit_1/bottleneck_v1/conv2/BatchNorm/moving_variance"]
+        msgs = net.check_variables(w)
+        assert any("moving_variance not found in checkpoint" in m for m in msgs)
+        with pytest.raises(ValueError, match="not found in checkpoint"):
+            net.load_weights(w, strict=True)
+        net.load_weights(w)                               # the non-strict path (synthetic weights, tests) is unchanged
+    finally:
+        network._REGISTRY[:] = before

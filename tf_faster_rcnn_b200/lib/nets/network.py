@@ -89,8 +89,26 @@ class Network(object):
         """14x14 crop + 2x2 max pool (network.py:154-157) unless a subclass crops 7x7 directly."""
         return True
 
-    def load_weights(self, tensors):
-        """tensors: dict TF-variable-name -> numpy array (HWIO convs, [in,out] FCs, BatchNorm stats)."""
+    def arch_name(self):
+        """'vgg16' | 'res50' | 'res101' | 'res152' | 'mobile' (the --net names of tools/test_net.py:92-103)."""
+        return {"vgg_16": "vgg16", "MobilenetV1": "mobile"}.get(self._scope) or "res%d" % self._num_layers
+
+    def check_variables(self, tensors):
+        """What tf.train.Saver.restore would reject: TEST-graph variables missing from `tensors` or of another shape
+        (class count, anchor set, backbone).  Needs create_architecture() first.  -> list of messages."""
+        from tf_faster_rcnn_b200 import synth
+        return synth.check(self.arch_name(), tensors, self._num_classes, self._num_anchors,
+                           rpn_channels=int(cfg.RPN_CHANNELS),
+                           depth_multiplier=float(getattr(self, "_depth_multiplier", 1.0)))
+
+    def load_weights(self, tensors, strict=False):
+        """tensors: dict TF-variable-name -> numpy array (HWIO convs, [in,out] FCs, BatchNorm stats).
+        strict: verify names and shapes against the architecture first (checkpoint restores) and raise ValueError."""
+        if strict:
+            problems = self.check_variables(tensors)
+            if problems:
+                raise ValueError("checkpoint does not match the %s TEST graph (%d classes, %d anchors):\n  %s"
+                                 % (self.arch_name(), self._num_classes, self._num_anchors, "\n  ".join(problems)))
         self.weights = engine.Weights(dict(tensors))
         self._plans = {}
 

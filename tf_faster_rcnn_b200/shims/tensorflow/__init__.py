@@ -39,8 +39,7 @@ class Session(object):
             from tf_faster_rcnn_b200 import synth
             for net in _networks():
                 if net.weights is None:
-                    name = {"vgg_16": "vgg16", "MobilenetV1": "mobile"}.get(net.scope) or "res%d" % net._num_layers
-                    net.load_weights(synth.make(name, net.num_classes, net.num_anchors))
+                    net.load_weights(synth.make(net.arch_name(), net.num_classes, net.num_anchors))
             return None
         raise NotImplementedError("tensorflow shim: Session.run only supports the variable initializer; "
                                   "inference goes through Network.test_image / im_detect")
@@ -62,7 +61,7 @@ class _Saver(object):
         from tf_faster_rcnn_b200 import checkpoint
         tensors = checkpoint.load_variables(save_path)
         for net in _networks():
-            net.load_weights(tensors)
+            net.load_weights(tensors, strict=True)         # missing keys / shape mismatches raise, as a TF restore does
 
 
 class _Train(object):

@@ -21,11 +21,17 @@ def _rng(seed, name):
 
 
 class _Gen:
-    def __init__(self, seed):
+    def __init__(self, seed, shapes_only=False):
         self.seed = seed
+        self.shapes_only = shapes_only          # record {name: shape} instead of drawing values (spec())
         self.w = {}
 
     def conv(self, name, kh, kw, cin, cout, std=None, bias=False, bias_std=0.01):
+        if self.shapes_only:
+            self.w[name + "/weights"] = (kh, kw, cin, cout)
+            if bias:
+                self.w[name + "/biases"] = (cout,)
+            return
         r = _rng(self.seed, name)
         s = np.sqrt(2.0 / (kh * kw * cin)) if std is None else std
         self.w[name + "/weights"] = (r.standard_normal((kh, kw, cin, cout)) * s).astype(F)
@@ -33,18 +39,29 @@ class _Gen:
             self.w[name + "/biases"] = (r.standard_normal(cout) * bias_std).astype(F)
 
     def dw(self, name, k, c):
+        if self.shapes_only:
+            self.w[name + "/depthwise_weights"] = (k, k, c, 1)
+            return
         r = _rng(self.seed, name)
         self.w[name + "/depthwise_weights"] = (r.standard_normal((k, k, c, 1)) * np.sqrt(2.0 / (k * k))).astype(F)
 
     def bn(self, name, c, gamma=(0.5, 1.5)):
-        r = _rng(self.seed, name + "/BatchNorm")
         p = name + "/BatchNorm/"
+        if self.shapes_only:
+            for leaf in ("gamma", "beta", "moving_mean", "moving_variance"):
+                self.w[p + leaf] = (c,)
+            return
+        r = _rng(self.seed, name + "/BatchNorm")
         self.w[p + "gamma"] = r.uniform(gamma[0], gamma[1], c).astype(F)
         self.w[p + "beta"] = (r.standard_normal(c) * 0.1).astype(F)
         self.w[p + "moving_mean"] = (r.standard_normal(c) * 0.1).astype(F)
         self.w[p + "moving_variance"] = r.uniform(0.5, 1.5, c).astype(F)
 
     def fc(self, name, cin, cout, std=None, bias_std=0.01):
+        if self.shapes_only:
+            self.w[name + "/weights"] = (cin, cout)
+            self.w[name + "/biases"] = (cout,)
+            return
         r = _rng(self.seed, name)
         s = np.sqrt(2.0 / cin) if std is None else std
         self.w[name + "/weights"] = (r.standard_normal((cin, cout)) * s).astype(F)
@@ -70,8 +87,8 @@ def resnet_block_plan(num_layers):
             ("block3", 256, [1] * n3), ("block4", 512, [1] * n4)]
 
 
-def make_vgg16(num_classes, num_anchors, seed=3):
-    g = _Gen(seed)
+def make_vgg16(num_classes, num_anchors, seed=3, shapes_only=False, rpn_channels=512):
+    g = _Gen(seed, shapes_only)
     cin = 3
     for b, (n, c) in enumerate([(2, 64), (2, 128), (3, 256), (3, 512), (3, 512)], start=1):
         for i in range(1, n + 1):
@@ -81,12 +98,12 @@ def make_vgg16(num_classes, num_anchors, seed=3):
             cin = c
     g.fc("vgg_16/fc6", 7 * 7 * 512, 4096)
     g.fc("vgg_16/fc7", 4096, 4096)
-    g.heads("vgg_16", 512, 4096, num_classes, num_anchors)
+    g.heads("vgg_16", 512, 4096, num_classes, num_anchors, rpn_channels)
     return g.w
 
 
-def make_resnet(num_layers, num_classes, num_anchors, seed=3):
-    g = _Gen(seed)
+def make_resnet(num_layers, num_classes, num_anchors, seed=3, shapes_only=False, rpn_channels=512):
+    g = _Gen(seed, shapes_only)
     sc = "resnet_v1_%d" % num_layers
     g.conv(sc + "/conv1", 7, 7, 3, 64, std=np.sqrt(2.0 / 147) / 60.0); g.bn(sc + "/conv1", 64)
     cin = 64
@@ -99,7 +116,7 @@ def make_resnet(num_layers, num_classes, num_anchors, seed=3):
             g.conv(p + "/conv2", 3, 3, base, base); g.bn(p + "/conv2", base)
             g.conv(p + "/conv3", 1, 1, base, base * 4); g.bn(p + "/conv3", base * 4, gamma=(0.1, 0.3))
             cin = base * 4
-    g.heads(sc, 1024, 2048, num_classes, num_anchors)
+    g.heads(sc, 1024, 2048, num_classes, num_anchors, rpn_channels)
     return g.w
 
 
@@ -112,8 +129,8 @@ def mobilenet_depth(d, mult=1.0, min_depth=8):
     return max(int(d * mult), min_depth)
 
 
-def make_mobilenet(num_classes, num_anchors, seed=3, mult=1.0):
-    g = _Gen(seed)
+def make_mobilenet(num_classes, num_anchors, seed=3, mult=1.0, shapes_only=False, rpn_channels=512):
+    g = _Gen(seed, shapes_only)
     sc = "MobilenetV1"
     cin = 3
     for i, (kind, _, d) in enumerate(MOBILENET_DEFS):
@@ -124,19 +141,41 @@ def make_mobilenet(num_classes, num_anchors, seed=3, mult=1.0):
             g.dw("%s/Conv2d_%d_depthwise" % (sc, i), 3, cin); g.bn("%s/Conv2d_%d_depthwise" % (sc, i), cin)
             g.conv("%s/Conv2d_%d_pointwise" % (sc, i), 1, 1, cin, c); g.bn("%s/Conv2d_%d_pointwise" % (sc, i), c)
         cin = c
-    g.heads(sc, mobilenet_depth(512, mult), mobilenet_depth(1024, mult), num_classes, num_anchors)
+    g.heads(sc, mobilenet_depth(512, mult), mobilenet_depth(1024, mult), num_classes, num_anchors, rpn_channels)
     return g.w
 
 
-def make(net, num_classes, num_anchors, seed=3):
+def make(net, num_classes, num_anchors, seed=3, shapes_only=False, rpn_channels=512, depth_multiplier=1.0):
     """net in {'vgg16','res50','res101','res152','mobile'} (tools/test_net.py:92-103 names)."""
     if net == "vgg16":
-        return make_vgg16(num_classes, num_anchors, seed)
+        return make_vgg16(num_classes, num_anchors, seed, shapes_only, rpn_channels)
     if net.startswith("res"):
-        return make_resnet(int(net[3:]), num_classes, num_anchors, seed)
+        return make_resnet(int(net[3:]), num_classes, num_anchors, seed, shapes_only, rpn_channels)
     if net == "mobile":
-        return make_mobilenet(num_classes, num_anchors, seed)
+        return make_mobilenet(num_classes, num_anchors, seed, depth_multiplier, shapes_only, rpn_channels)
     raise ValueError(net)
+
+
+def spec(net, num_classes, num_anchors, **arch):
+    """{TF variable name: shape} the TEST graph of `net` restores (the variables `make` draws), without drawing them.
+    arch: rpn_channels (cfg.RPN_CHANNELS), depth_multiplier (cfg.MOBILENET.DEPTH_MULTIPLIER)."""
+    return make(net, num_classes, num_anchors, shapes_only=True, **arch)
+
+
+def check(net, tensors, num_classes, num_anchors, limit=12, **arch):
+    """Problems that would make `Saver.restore` fail in the reference: variables of the TEST graph that are missing from
+    `tensors`, or present with another shape (wrong class count / anchor set / backbone).  Extra variables (optimizer
+    slots, global_step) are ignored, as a restore ignores them.  Returns a list of messages, empty when compatible."""
+    problems = []
+    for name, shape in spec(net, num_classes, num_anchors, **arch).items():
+        if name not in tensors:
+            problems.append("Key %s not found in checkpoint" % name)
+        elif tuple(np.shape(tensors[name])) != tuple(shape):
+            problems.append("%s: checkpoint has shape %s, the %s graph for %d classes / %d anchors needs %s"
+                            % (name, list(np.shape(tensors[name])), net, num_classes, num_anchors, list(shape)))
+    if len(problems) > limit:
+        problems = problems[:limit] + ["... and %d more" % (len(problems) - limit)]
+    return problems
 
 
 def synthetic_blob(h, w, seed=3):
