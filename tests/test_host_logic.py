@@ -281,3 +281,28 @@ def test_reference_demo_script_drives_this_lib_unchanged(tmp_path):
     assert "Loaded network" in out, out[-2000:]
     assert "Demo for data/demo/000456.jpg" in out, out[-2000:]
     assert "check_device failed" in out and "no CUDA device" in out, out[-2000:]
+
+
+def test_nms_module_surface_routes_to_the_device_entry(monkeypatch):
+    """nms.gpu_nms / nms.cpu_nms / nms.py_cpu_nms (the reference's import surface) sort on the host, call the
+    `_nms`-compatible device entry with the right predicate flags, and map kept positions back to input indices."""
+    from tf_faster_rcnn_b200 import ops, _native as N
+    from nms.gpu_nms import gpu_nms
+    from nms.cpu_nms import cpu_nms
+    from nms.py_cpu_nms import py_cpu_nms
+    calls = []
+
+    def fake(sorted_dets, thresh, flags, device_id=0):
+        calls.append((np.array(sorted_dets), thresh, flags, device_id))
+        return np.array([0, 2], dtype=np.int32)              # keep the best and the third best
+    monkeypatch.setattr(ops, "nms_host", fake)
+    dets = np.array([[0, 0, 9, 9, 0.2], [1, 1, 8, 8, 0.9], [2, 2, 7, 7, 0.5], [3, 3, 6, 6, 0.9]], np.float32)
+    assert gpu_nms(dets, 0.3, device_id=0) == [1, 2]          # order = [1, 3, 2, 0] (tie 0.9: lower index first)
+    assert calls[-1][0][:, 4].tolist() == pytest.approx([0.9, 0.9, 0.5, 0.2]) and calls[-1][2] == N.NMS_MODE_GPU_NMS
+    assert calls[-1][1] == float(np.float32(0.3))
+    assert cpu_nms(dets, 0.3) == [1, 2] and calls[-1][2] == N.NMS_MODE_CPU_NMS
+    assert calls[-1][1] == float(np.float32(0.3))             # f32(0.3) > 0.3: '>= 0.3 (double)' == '>= f32(0.3)'
+    cpu_nms(dets, 0.7)
+    assert calls[-1][1] == float(np.nextafter(np.float32(0.7), np.float32(1)))    # f32(0.7) < 0.7: next fp32 up
+    assert py_cpu_nms(dets, 0.3) == [1, 2] and calls[-1][2] == N.NMS_MODE_GPU_NMS
+    assert gpu_nms(np.zeros((0, 5), np.float32), 0.3) == [] and cpu_nms(np.zeros((0, 5), np.float32), 0.3) == []
