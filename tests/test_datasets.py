@@ -231,3 +231,70 @@ def test_reval_tool_rescoring_from_detections_pkl(tmp_path):
     assert r.returncode == 0, r.stderr[-2000:]
     assert "Mean AP = " in r.stdout and "AP for person = " in r.stdout
     assert os.path.isfile(os.path.join(devkit, "results", "VOC2007", "Main", "comp4_det_test_dog.txt"))
+
+
+def test_coco_bbox_eval_against_a_plain_loop_implementation():
+    """Randomised cross-check of the vectorised scorer against a deliberately naive re-statement (python loops, one IoU
+    threshold at a time, no crowds / area filters): same protocol, independent code."""
+    from datasets.coco_eval import BboxEval, IOU_THRS, REC_THRS
+
+    def iou(a, b):
+        iw = min(a[0] + a[2], b[0] + b[2]) - max(a[0], b[0])
+        ih = min(a[1] + a[3], b[1] + b[3]) - max(a[1], b[1])
+        inter = max(iw, 0.0) * max(ih, 0.0)
+        return inter / (a[2] * a[3] + b[2] * b[3] - inter)
+
+    def naive_ap(gt, dt, imgs, thr):
+        rows, npos = [], 0                                     # (score, is_tp) over all images
+        for img in imgs:
+            g = [a["bbox"] for a in gt.get(img, [])]
+            d = sorted([x for x in dt if x["image_id"] == img], key=lambda x: -x["score"])[:100]
+            npos += len(g)
+            taken = [False] * len(g)
+            for x in d:
+                best, m = min(thr, 1 - 1e-10), -1
+                for j, gb in enumerate(g):
+                    if taken[j]:
+                        continue
+                    v = iou(x["bbox"], gb)
+                    if v >= best:
+                        best, m = v, j
+                if m >= 0:
+                    taken[m] = True
+                rows.append((x["score"], m >= 0))
+        order = sorted(range(len(rows)), key=lambda i: -rows[i][0])       # python's sort is stable, like mergesort
+        tp = fp = 0
+        rc, pr = [], []
+        for i in order:
+            tp += rows[i][1]
+            fp += not rows[i][1]
+            rc.append(tp / npos)
+            pr.append(tp / (tp + fp + np.spacing(1)))
+        for i in range(len(pr) - 1, 0, -1):
+            pr[i - 1] = max(pr[i - 1], pr[i])
+        q = []
+        for r in REC_THRS:
+            idx = next((i for i, v in enumerate(rc) if v >= r), None)
+            q.append(pr[idx] if idx is not None else 0.0)
+        return float(np.mean(q))
+
+    rng = np.random.default_rng(11)
+    for trial in range(3):
+        imgs = list(range(1, 7))
+        gt, dt = {}, []
+        for img in imgs:
+            for _ in range(int(rng.integers(0, 5))):
+                x, y = rng.uniform(0, 300, 2)
+                w, h = rng.uniform(40, 120, 2)                 # all 'medium'/'large': inside the 'all' range either way
+                gt.setdefault(img, []).append({"image_id": img, "category_id": 1, "bbox": [x, y, w, h], "area": w * h, "iscrowd": 0})
+                for _ in range(int(rng.integers(0, 3))):       # detections scattered around the object
+                    j = rng.normal(0, 14, 4)
+                    dt.append({"image_id": img, "category_id": 1, "bbox": [x + j[0], y + j[1], max(w + j[2], 5), max(h + j[3], 5)],
+                               "score": float(rng.random())})
+            for _ in range(int(rng.integers(0, 3))):
+                x, y = rng.uniform(0, 300, 2)
+                dt.append({"image_id": img, "category_id": 1, "bbox": [x, y, 60.0, 60.0], "score": float(rng.random())})
+        ev = BboxEval(gt, dt, [1], imgs).evaluate()
+        for t, thr in enumerate(IOU_THRS):
+            got = float(np.mean(ev.precision[t, :, 0, 0, 2]))
+            assert got == pytest.approx(naive_ap(gt, dt, imgs, thr), abs=1e-12), (trial, thr)
