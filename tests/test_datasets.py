@@ -298,3 +298,29 @@ def test_coco_bbox_eval_against_a_plain_loop_implementation():
         for t, thr in enumerate(IOU_THRS):
             got = float(np.mean(ev.precision[t, :, 0, 0, 2]))
             assert got == pytest.approx(naive_ap(gt, dt, imgs, thr), abs=1e-12), (trial, thr)
+
+
+def test_ds_utils_helpers():
+    from datasets import ds_utils as du
+    boxes = np.array([[10, 20, 30, 40], [10, 20, 30, 40], [0, 0, 5, 9], [10.2, 20.4, 30.1, 39.6]], np.float32)
+    assert du.unique_boxes(boxes).tolist() == [0, 2] and du.unique_boxes(boxes, scale=10).tolist() == [0, 2, 3]
+    assert du.xywh_to_xyxy(np.array([[2, 3, 4, 5]])).tolist() == [[2, 3, 5, 7]]
+    assert du.xyxy_to_xywh(du.xywh_to_xyxy(np.array([[2, 3, 4, 5]]))).tolist() == [[2, 3, 4, 5]]
+    assert du.filter_small_boxes(boxes, 9).tolist() == [0, 1, 3]           # w >= 9 and h > 9 (the reference's asymmetry)
+    du.validate_boxes(np.array([[0, 0, 4, 4]]), width=5, height=5)
+    with pytest.raises(AssertionError):
+        du.validate_boxes(np.array([[0, 0, 5, 4]]), width=5, height=5)
+    ref_path = "/root/reference/lib/datasets/ds_utils.py"
+    if os.path.isfile(ref_path):                                            # differential check where the reference exists
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("ref_ds_utils", ref_path)
+        ref = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(ref)
+        rng = np.random.default_rng(5)
+        b = rng.integers(0, 40, (200, 4)).astype(np.float64)
+        b[:, 2:] += b[:, :2]
+        b = np.vstack([b, b[:50]])
+        assert np.array_equal(du.unique_boxes(b), ref.unique_boxes(b))
+        assert np.array_equal(du.unique_boxes(b, 0.25), ref.unique_boxes(b, 0.25))
+        assert np.array_equal(du.xywh_to_xyxy(b), ref.xywh_to_xyxy(b)) and np.array_equal(du.xyxy_to_xywh(b), ref.xyxy_to_xywh(b))
+        assert np.array_equal(du.filter_small_boxes(b, 12), ref.filter_small_boxes(b, 12))
