@@ -1,9 +1,12 @@
 #!/usr/bin/env python
-"""Re-score a finished test_net run from its detections.pkl (counterpart of the reference's tools/reval.py:24-75; same
-arguments).  `--nms` first re-applies per-class NMS at cfg.TEST.NMS through model.test.apply_nms (GPU);
-without it the script is CPU-only.
+"""Score an existing test_net run again from the `detections.pkl` it left in its output directory -- the command line of
+the reference's tools/reval.py:24-75 (positional output dir, --imdb, --matlab, --comp, --nms), plus `--set K V ...` for cfg
+overrides such as DATA_DIR.
 
-    python tools/reval.py <output_dir> --imdb voc_2007_test [--comp] [--nms] [--set DATA_DIR /data ...]"""
+    python tools/reval.py output/default/voc_2007_test/default --imdb voc_2007_test --comp
+
+With --nms every class is first put through model.test.apply_nms at cfg.TEST.NMS (that step needs the GPU); otherwise
+the script only touches the CPU."""
 import argparse
 import os
 import pickle
@@ -11,40 +14,56 @@ import sys
 
 import _init_paths  # noqa: F401
 
-from model.config import cfg, cfg_from_list
 from datasets.factory import get_imdb
+from model.config import cfg, cfg_from_list
+
+FLAGS = (("--matlab", "matlab_eval", "evaluate with the MATLAB devkit (not provided here)"),
+         ("--comp", "comp_mode", "competition mode: fixed result-file names, files are kept"),
+         ("--nms", "apply_nms", "re-apply per-class NMS before scoring"))
 
 
-def parse_args(argv=None):
-    p = argparse.ArgumentParser(description="Re-evaluate results")
-    p.add_argument("output_dir", nargs=1, type=str, help="results directory holding detections.pkl")
-    p.add_argument("--imdb", dest="imdb_name", default="voc_2007_test", type=str)
-    p.add_argument("--matlab", dest="matlab_eval", action="store_true")
-    p.add_argument("--comp", dest="comp_mode", action="store_true")
-    p.add_argument("--nms", dest="apply_nms", action="store_true")
-    p.add_argument("--set", dest="set_cfgs", default=None, nargs=argparse.REMAINDER)
-    if argv is None and len(sys.argv) == 1:
-        p.print_help()
-        sys.exit(1)
-    return p.parse_args(argv)
+def build_parser():
+    parser = argparse.ArgumentParser(description="Re-evaluate results")
+    parser.add_argument("output_dir", nargs=1, type=str, help="directory that holds detections.pkl")
+    parser.add_argument("--imdb", dest="imdb_name", type=str, default="voc_2007_test", help="dataset to score against")
+    for flag, dest, text in FLAGS:
+        parser.add_argument(flag, dest=dest, action="store_true", help=text)
+    parser.add_argument("--set", dest="set_cfgs", nargs=argparse.REMAINDER, default=None, help="cfg overrides: KEY VALUE ...")
+    return parser
 
 
-def from_dets(imdb_name, output_dir, args):
-    imdb = get_imdb(imdb_name)
-    imdb.competition_mode(args.comp_mode)
-    imdb.config["matlab_eval"] = args.matlab_eval
-    with open(os.path.join(output_dir, "detections.pkl"), "rb") as f:
-        dets = pickle.load(f)
-    if args.apply_nms:
+def load_detections(output_dir):
+    path = os.path.join(output_dir, "detections.pkl")
+    with open(path, "rb") as f:
+        return pickle.load(f)
+
+
+def rescore(imdb_name, output_dir, comp_mode=False, matlab_eval=False, nms=False):
+    """all_boxes from <output_dir>/detections.pkl -> imdb.evaluate_detections; returns what the imdb returns."""
+    dataset = get_imdb(imdb_name)
+    dataset.competition_mode(comp_mode)
+    dataset.config["matlab_eval"] = matlab_eval
+    all_boxes = load_detections(output_dir)
+    if nms:
         from model.test import apply_nms
         print("Applying NMS to all detections")
-        dets = apply_nms(dets, cfg.TEST.NMS)
+        all_boxes = apply_nms(all_boxes, cfg.TEST.NMS)
     print("Evaluating detections")
-    return imdb.evaluate_detections(dets, output_dir)
+    return dataset.evaluate_detections(all_boxes, output_dir)
+
+
+def main(argv=None):
+    parser = build_parser()
+    argv = sys.argv[1:] if argv is None else argv
+    if not argv:
+        parser.print_help()
+        return 1
+    args = parser.parse_args(argv)
+    if args.set_cfgs:
+        cfg_from_list(args.set_cfgs)
+    rescore(args.imdb_name, os.path.abspath(args.output_dir[0]), args.comp_mode, args.matlab_eval, args.apply_nms)
+    return 0
 
 
 if __name__ == "__main__":
-    a = parse_args()
-    if a.set_cfgs:
-        cfg_from_list(a.set_cfgs)
-    from_dets(a.imdb_name, os.path.abspath(a.output_dir[0]), a)
+    sys.exit(main())
