@@ -76,11 +76,13 @@ int frcnn_nms_sorted_dev(const float* boxes_dev, int n, float thresh, unsigned f
  *                          * scale[co] + shift[co] (+ residual[n,ho,wo,co]) )
  * Requirements: cin % 32 == 0.  w_hi/w_lo from frcnn_pack_conv_weights.  scale may be NULL (=1). */
 typedef struct frcnn_conv_plan frcnn_conv_plan;
+#define FRCNN_CONV_F16X3 0   /* fp16 hi/lo split of both operands, 3 x tcgen05.mma.kind::f16, fp32 accumulate */
+#define FRCNN_CONV_TF32X3 1  /* tf32 hi/lo split, 3 x kind::tf32 (same 22-bit products, twice the tensor time) */
 
 typedef struct {
   const float* in_dev;       /* [n, h, w, cin] */
-  const float* w_hi_dev;     /* [cout, kh*kw*cin] tf32-rounded weights */
-  const float* w_lo_dev;     /* [cout, kh*kw*cin] tf32-rounded residual w - w_hi */
+  const void* w_hi_dev;      /* [cout, kh*kw*cin] hi plane from frcnn_pack_conv_weights (fp16) / _tf32 (fp32) */
+  const void* w_lo_dev;      /* [cout, kh*kw*cin] lo plane (residual of the hi rounding) */
   const float* scale_dev;    /* [cout] or NULL */
   const float* shift_dev;    /* [cout] or NULL */
   const float* residual_dev; /* [n, ho, wo, cout] or NULL */
@@ -93,6 +95,8 @@ typedef struct {
   int block_n;               /* 0 = choose; else 64/128 */
   int kb_per_chunk;          /* 0 = default (8): 32-wide k-blocks summed in TMEM before promotion to registers */
   int split_k;               /* 0 = choose; 1 = never; n = split the K loop over n CTAs + deterministic reduce pass */
+  int impl;                  /* FRCNN_CONV_F16X3 (0, default) | FRCNN_CONV_TF32X3 (r01 kernel, kept for A/B measurements) */
+  float out_mult;            /* F16X3: 2^-wexp of frcnn_pack_conv_weights (0 is read as 1) */
 } frcnn_conv_desc;
 
 int frcnn_conv_plan_create(frcnn_conv_plan** out, const frcnn_conv_desc* d);
@@ -108,10 +112,19 @@ int frcnn_conv_plan_info(const frcnn_conv_plan* p, int* block_n, int* tile_n, in
  * [3]=splitter arrived, [4]=MMA saw operands, [5]=MMAs issued+committed, [chunk][7]=epilogue saw TMEM chunk. NULL disables. */
 int frcnn_conv_plan_set_trace(frcnn_conv_plan* p, long long* trace_dev);
 void frcnn_conv_plan_destroy(frcnn_conv_plan* p);
+/* development aid: in the watchdog build (libfrcnn_b200_wd.so, -DFRCNN_WATCHDOG) a barrier wait of the dense kernel that
+ * lasts > ~0.2 s aborts the kernel instead of hanging the GPU; out16 = {aborted, waits_timed_out, block, thread, wait_tag,
+ * parity, aux, ...}.  In the normal build out16[15] = 0xffffffff and the rest is zero. */
+int frcnn_debug_watchdog(unsigned int* out16, int reset);
 
-/* HWIO [kh,kw,cin,cout] (TF layout) -> K-major [cout][kh][kw][cin], split into tf32 hi/lo planes. */
-int frcnn_pack_conv_weights(const float* w_hwio_dev, float* w_hi_dev, float* w_lo_dev, int kh, int kw,
-                            int cin, int cout, void* stream);
+/* HWIO [kh,kw,cin,cout] (TF layout) -> K-major [cout][kh][kw][cin] fp16 planes:
+ *   hi = RN_f16(w * 2^wexp), lo = RN_f16((w * 2^wexp - hi) * 2^11).  The caller picks wexp so that max|w| * 2^wexp lies in
+ * [2^13, 2^14) and passes out_mult = 2^-wexp in the conv descriptor. */
+int frcnn_pack_conv_weights(const float* w_hwio_dev, void* w_hi_dev, void* w_lo_dev, int kh, int kw,
+                            int cin, int cout, int wexp, void* stream);
+/* same layout, fp32 planes of tf32-rounded values (hi = RN_tf32(w), lo = RN_tf32(w - hi)) for FRCNN_CONV_TF32X3 */
+int frcnn_pack_conv_weights_tf32(const float* w_hwio_dev, float* w_hi_dev, float* w_lo_dev, int kh, int kw,
+                                 int cin, int cout, void* stream);
 
 /* ---- (3) bandwidth stages (SIMT, fp32, no FMA contraction where the oracle has separate roundings) ---- */
 /* first-layer convolution for cin==3 (vgg conv1_1, resnet conv1 7x7/2, mobilenet Conv2d_0 3x3/2):

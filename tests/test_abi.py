@@ -49,7 +49,7 @@ def test_conv_desc_struct_matches_header():
         decl = decl.strip()
         if not decl:
             continue
-        decl = re.sub(r"^(const\s+)?(float\*|int)\s*", "", decl)
+        decl = re.sub(r"^(const\s+)?(float\*|void\*|float|int)\s*", "", decl)
         fields += [f.strip().lstrip("*") for f in decl.split(",")]
     assert fields == [f[0] for f in _native.ConvDesc._fields_]
 

@@ -7,13 +7,15 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfrcnn_b200.so")
+# FRCNN_LIB_VARIANT=wd selects the development build with barrier-wait watchdogs (tools only; never the default)
+LIB_PATH = os.path.join(_HERE, "libfrcnn_b200_wd.so" if os.environ.get("FRCNN_LIB_VARIANT") == "wd" else "libfrcnn_b200.so")
 
 NMS_PLUS_ONE, NMS_INCLUSIVE, NMS_SKIP_DEGENERATE = 1, 2, 4
 NMS_MODE_CPU_NMS = NMS_PLUS_ONE | NMS_INCLUSIVE
 NMS_MODE_GPU_NMS = NMS_PLUS_ONE
 NMS_MODE_TF = NMS_SKIP_DEGENERATE
 ACT_NONE, ACT_RELU, ACT_RELU6 = 0, 1, 2
+CONV_F16X3, CONV_TF32X3 = 0, 1
 
 vp, ci, cf, cu, sz = C.c_void_p, C.c_int, C.c_float, C.c_uint, C.c_size_t
 ip, fp = C.POINTER(C.c_int), C.POINTER(C.c_float)
@@ -24,7 +26,8 @@ class ConvDesc(C.Structure):
     _fields_ = [("in_dev", vp), ("w_hi_dev", vp), ("w_lo_dev", vp), ("scale_dev", vp), ("shift_dev", vp),
                 ("residual_dev", vp), ("out_dev", vp),
                 ("n", ci), ("h", ci), ("w", ci), ("cin", ci), ("cout", ci), ("kh", ci), ("kw", ci), ("stride", ci),
-                ("pad_t", ci), ("pad_l", ci), ("ho", ci), ("wo", ci), ("act", ci), ("block_n", ci), ("kb_per_chunk", ci), ("split_k", ci)]
+                ("pad_t", ci), ("pad_l", ci), ("ho", ci), ("wo", ci), ("act", ci), ("block_n", ci), ("kb_per_chunk", ci), ("split_k", ci),
+                ("impl", ci), ("out_mult", cf)]
 
 
 # name -> (restype, argtypes); must list every symbol of include/frcnn_b200.h (checked by tests/test_abi.py)
@@ -40,7 +43,9 @@ SIGNATURES = {
     "frcnn_conv_plan_info": (ci, [vp, ip, ip, ip, ip, ip, ip, ip, ip]),
     "frcnn_conv_plan_set_trace": (ci, [vp, vp]),
     "frcnn_conv_plan_destroy": (None, [vp]),
-    "frcnn_pack_conv_weights": (ci, [vp, vp, vp, ci, ci, ci, ci, vp]),
+    "frcnn_debug_watchdog": (ci, [C.POINTER(C.c_uint), ci]),
+    "frcnn_pack_conv_weights": (ci, [vp, vp, vp, ci, ci, ci, ci, ci, vp]),
+    "frcnn_pack_conv_weights_tf32": (ci, [vp, vp, vp, ci, ci, ci, ci, vp]),
     "frcnn_conv_first": (ci, [vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp]),
     "frcnn_depthwise3x3": (ci, [vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp]),
     "frcnn_max_pool": (ci, [vp, vp, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp]),

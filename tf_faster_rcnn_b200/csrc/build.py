@@ -25,8 +25,11 @@ def _stale(dst, srcs):
     return any(os.path.getmtime(s) > t for s in srcs)
 
 
-def build(force=False, verbose=False):
-    obj_dir = os.path.join(HERE, "_obj")
+def build(force=False, verbose=False, watchdog=False):
+    """watchdog=True builds libfrcnn_b200_wd.so (-DFRCNN_WATCHDOG: barrier waits that time out instead of hanging)."""
+    obj_dir = os.path.join(HERE, "_obj_wd" if watchdog else "_obj")
+    lib = LIB.replace(".so", "_wd.so") if watchdog else LIB
+    flags = NVCC_FLAGS + (["-DFRCNN_WATCHDOG"] if watchdog else [])
     os.makedirs(obj_dir, exist_ok=True)
     hdrs = [os.path.join(HERE, h) for h in HEADERS]
     jobs = []
@@ -38,7 +41,7 @@ def build(force=False, verbose=False):
 
     def cc(job):
         src, obj = job
-        r = subprocess.run(["nvcc"] + NVCC_FLAGS + ["-c", src, "-o", obj], capture_output=True, text=True)
+        r = subprocess.run(["nvcc"] + flags + ["-c", src, "-o", obj], capture_output=True, text=True)
         log = r.stdout + r.stderr
         with open(obj + ".log", "w") as f:
             f.write(log)
@@ -52,11 +55,11 @@ def build(force=False, verbose=False):
         for l in logs:
             print(l)
     objs = [os.path.join(obj_dir, s.replace(".cu", ".o")) for s in SOURCES]
-    if force or jobs or _stale(LIB, objs):
+    if force or jobs or _stale(lib, objs):
         subprocess.check_call(["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static",
-                               "-o", LIB] + objs)
-    return LIB
+                               "-o", lib] + objs)
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    print(build(force="--force" in sys.argv, verbose=True, watchdog="--watchdog" in sys.argv))

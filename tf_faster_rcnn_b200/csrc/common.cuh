@@ -53,6 +53,10 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// arrive that the compiler must order after the computation of `dep` (an otherwise unused register operand)
+__device__ __forceinline__ void mbar_arrive_after(uint64_t* bar, uint32_t dep) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0]; // after %1" ::"r"(smem_u32(bar)), "r"(dep) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t addr = smem_u32(bar);
   asm volatile(
@@ -63,6 +67,42 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "bra WAIT_LOOP;\n\t"
       "WAIT_DONE:\n\t}\n" ::"r"(addr), "r"(parity) : "memory");
 }
+
+// ---- development watchdog (builds with -DFRCNN_WATCHDOG only: libfrcnn_b200_wd.so) -------------------------------------
+// A barrier-protocol bug in a warp-specialised kernel shows up as a hang, which on a leased GPU box is a lost call with no
+// information.  In watchdog builds every tagged wait gives up after ~0.2 s, records who waited on what, and raises a
+// device-wide abort flag that makes every other tagged wait fall through, so the kernel terminates (with garbage) and the
+// host can read the record through frcnn_debug_watchdog().  Normal builds compile MBAR_WAIT to the plain wait.
+#ifdef FRCNN_WATCHDOG
+static __device__ unsigned int g_watchdog[16];   // per translation unit (only conv_gemm.cu uses it)
+//   // [0] abort flag, [1] count, [2..7] first record: block, thread, tag, parity, kbt, spare
+__device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity, uint32_t tag, uint32_t aux) {
+  const uint32_t addr = smem_u32(bar);
+  long long t0 = 0;
+  for (uint32_t it = 0;; ++it) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred P;\n\tmbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\tselp.u32 %0, 1, 0, P;\n\t}\n"
+                 : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    if (ok) return;
+    if ((it & 63u) == 63u) {
+      if (*(volatile unsigned int*)&g_watchdog[0]) return;
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 400000000LL) {
+        if (atomicAdd(&g_watchdog[1], 1u) == 0u) {
+          g_watchdog[2] = blockIdx.x; g_watchdog[3] = threadIdx.x; g_watchdog[4] = tag; g_watchdog[5] = parity; g_watchdog[6] = aux;
+        }
+        __threadfence();
+        atomicExch(&g_watchdog[0], 1u);
+        return;
+      }
+    }
+  }
+}
+#define MBAR_WAIT(bar, parity, tag, aux) mbar_wait_wd(bar, parity, tag, (uint32_t)(aux))
+#else
+#define MBAR_WAIT(bar, parity, tag, aux) mbar_wait(bar, parity)
+#endif
 
 // tcgen05 fences around thread synchronisation ---------------------------------------------------
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -102,6 +142,24 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, u
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n"
       ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// D[tmem] (+)= A * B, FP16 operands (K = 16 per instruction), fp32 accumulate, single CTA; A from tensor memory (lane = row,
+// one 32-bit column per PAIR of K-consecutive fp16 values: 8 columns per instruction), B from shared memory
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// register re-allocation between warp roles: every warp of a warpgroup (4 consecutive warps) executes the same one
+template <int R> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
+template <int R> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R)); }
+// two fp32 -> packed fp16x2 (lo half = a, hi half = b), round to nearest even, saturating to +-65504
+__device__ __forceinline__ uint32_t pack_f16x2_sat(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
 }
 // arrive on an mbarrier once all previously issued MMAs of this thread have completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {

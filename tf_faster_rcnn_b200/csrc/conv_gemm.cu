@@ -39,6 +39,7 @@
 // cross terms a_lo*b_hi + a_hi*b_lo over the WHOLE k loop (2^-11 of the result, so its truncation is harmless and it is
 // read once per tile); [256, 512) A ring: slot s = 32 cols hi + 32 cols lo.  Only D_main is promoted per chunk, and it
 // takes 4 instead of 12 truncating adds per k-block, so the chunk can be 3x longer for the same error.
+#include <cuda_fp16.h>
 #include "common.cuh"
 #include "../../include/frcnn_b200.h"
 #include <stdlib.h>
@@ -76,6 +77,7 @@ struct ConvKernelParams {
   int m_tiles, n_tiles, total_units, n_full, splits;
   float* ws;
   long long* trace;   // debug: clock64() stamps of CTA (0,0)'s pipeline hand-offs; normally NULL
+  float out_mult;     // f16x3: 2^-wexp, undoes the power-of-two weight scaling (exact); tf32x3: 1
 };
 
 #define FRCNN_TRACE2(base, idx)                                                             \
@@ -122,6 +124,118 @@ __device__ __forceinline__ Unit decode_unit(const ConvKernelParams& p, int u, in
   if (t.slot < 0) { t.kb0 = 0; t.num_kb = num_kb_total; }
   else { t.kb0 = t.z * p.kb_per_split; t.num_kb = min(p.kb_per_split, num_kb_total - t.kb0); }
   return t;
+}
+
+// ---------------- tile epilogue shared by both kernels (overlaps the next unit's main loop) ----------------
+// `acc` = this thread's W = BN/2 fp32 sums of output row (q*32 + lane), columns [col0, col0 + W) of the tile; ew = index of the
+// epilogue warp (0..7) = its 4 KB slice of the transposition buffer.
+template <int BN>
+__device__ __forceinline__ void epilogue_tile(const ConvKernelParams& p, const Unit& t, const float (&acc)[BN / 2],
+                                              uint8_t* smem_stage, int ew, int q, int lane) {
+  constexpr int W = BN / 2;
+  const int col0 = (ew >> 2) * W;
+  const float om = p.out_mult;
+  // r01 finding 4: writing each thread's own output row straight from registers (32 lanes = 32 rows, 8 KB apart) made
+  // every global access 32 separate sectors.  The tile is transposed through shared memory 32 columns at a time: thread =
+  // row writes XOR-swizzled 16-byte chunks (conflict free), then each lane owns 4 fixed channels and walks the warp's rows
+  // with coalesced 128-bit accesses (one full 128-byte line per row).  r01 finding 5: epilogue inputs are loaded with
+  // pinned (asm volatile) loads -- with __ldg the compiler sank the scale/shift loads into the row loop.
+  constexpr int CH = 8;                                   // 16-byte chunks per staged 32-column row
+  constexpr int ROWS_PER_IT = 4;
+  constexpr int ITERS = 8;
+  float4* stage = reinterpret_cast<float4*>(smem_stage + ew * (32 * 32 * 4));
+  const int row = q * 32 + lane;
+  const int rows_img = p.th * p.tw;
+  const int dn = row / rows_img, rem = row % rows_img;
+  const int dh = rem / p.tw, dw = rem % p.tw;
+  const int n = t.n0 + dn, h = t.h0 + dh, w = t.w0 + dw;
+  const bool valid = (row < p.tn * rows_img) && n < p.nimg && h < p.ho && w < p.wo;
+  const int cg = lane & (CH - 1);                         // column group of this lane
+  const int rsub = lane >> 3;
+  if (t.slot >= 0) {
+    // split tile: plain partial sums in the tile-local [128][BN] workspace layout; the epilogue runs in tail_reduce_kernel
+    float* const wbase = p.ws + ((size_t)t.slot * p.splits + t.z) * (size_t)(BLOCK_M * BN) + (size_t)(q * 32) * BN + col0;
+#pragma unroll
+    for (int pass = 0; pass < W / 32; ++pass) {
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < CH; ++j) {
+        const int a0 = pass * 32 + 4 * j;
+        stage[lane * CH + ((j ^ lane) & (CH - 1))] =
+            make_float4(__fmul_rn(acc[a0], om), __fmul_rn(acc[a0 + 1], om), __fmul_rn(acc[a0 + 2], om), __fmul_rn(acc[a0 + 3], om));
+      }
+      __syncwarp();
+#pragma unroll
+      for (int it = 0; it < ITERS; ++it) {
+        const int r = it * ROWS_PER_IT + rsub;
+        *reinterpret_cast<float4*>(wbase + (size_t)r * BN + pass * 32 + cg * 4) = stage[r * CH + ((cg ^ r) & (CH - 1))];
+      }
+    }
+    return;
+  }
+  const int my_pix = valid ? (int)(((long long)n * p.ho + h) * p.wo + w) : -1;
+  const bool vec_ok = (p.cout & 3) == 0;
+  float* const obase = p.out;
+  const float* const rbase = p.residual;
+  const float* const scale = p.scale;
+  const float* const shift = p.shift;
+  const int act = p.act;
+  int pixr[ITERS];
+#pragma unroll
+  for (int it = 0; it < ITERS; ++it) pixr[it] = __shfl_sync(0xffffffffu, my_pix, it * ROWS_PER_IT + rsub);
+#pragma unroll
+  for (int pass = 0; pass < W / 32; ++pass) {
+    const int c = t.nblk * BN + col0 + pass * 32 + cg * 4;   // first of this lane's 4 output channels in this pass
+    const bool col_ok = c < p.cout;
+    float sc[4] = {1.f, 1.f, 1.f, 1.f}, sh[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      if (c + e < p.cout) {
+        if (scale) sc[e] = ld_nc_f32_pinned(scale + c + e);
+        if (shift) sh[e] = ld_nc_f32_pinned(shift + c + e);
+      }
+    float4 rv[ITERS];
+    const bool res_vec = rbase && vec_ok;
+    if (res_vec) {
+#pragma unroll
+      for (int it = 0; it < ITERS; ++it)
+        rv[it] = (pixr[it] >= 0 && col_ok) ? ld_nc_f4_pinned(rbase + (size_t)pixr[it] * p.cout + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncwarp();                                           // previous pass's reads are done
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+      const int a0 = pass * 32 + 4 * j;
+      stage[lane * CH + ((j ^ lane) & (CH - 1))] = make_float4(acc[a0], acc[a0 + 1], acc[a0 + 2], acc[a0 + 3]);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+      if (pixr[it] < 0 || !col_ok) continue;
+      const int r = it * ROWS_PER_IT + rsub;
+      const float4 v = stage[r * CH + ((cg ^ r) & (CH - 1))];
+      float y[4] = {v.x, v.y, v.z, v.w};
+      float res[4] = {0.f, 0.f, 0.f, 0.f};
+      if (res_vec) { res[0] = rv[it].x; res[1] = rv[it].y; res[2] = rv[it].z; res[3] = rv[it].w; }
+      float* optr = obase + (size_t)pixr[it] * p.cout + c;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float a = __fmul_rn(y[e], om);   // exact: power of two
+        if (scale) a = __fmul_rn(a, sc[e]);
+        if (shift) a = __fadd_rn(a, sh[e]);
+        if (res_vec) a = __fadd_rn(a, res[e]);
+        else if (rbase && c + e < p.cout) a = __fadd_rn(a, __ldg(rbase + (size_t)pixr[it] * p.cout + c + e));
+        if (act == FRCNN_ACT_RELU) a = fmaxf(a, 0.f);
+        else if (act == FRCNN_ACT_RELU6) a = fminf(fmaxf(a, 0.f), 6.f);
+        y[e] = a;
+      }
+      if (vec_ok) {
+        *reinterpret_cast<float4*>(optr) = make_float4(y[0], y[1], y[2], y[3]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) if (c + e < p.cout) optr[e] = y[e];
+      }
+    }
+  }
 }
 
 template <int BN>
@@ -335,107 +449,7 @@ conv_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         if (threadIdx.x == 128) FRCNN_TRACE2(512, ct);
       }
       if (threadIdx.x == 128) FRCNN_TRACE2(702, 0);
-      // ---------------- epilogue (overlaps the next unit's main loop) ----------------
-      // r01 finding 4: writing each thread's own output row straight from registers (32 lanes = 32 rows, 8 KB apart) made
-      // every global access 32 separate sectors.  The tile is transposed through shared memory 32 columns at a time: thread =
-      // row writes XOR-swizzled 16-byte chunks (conflict free), then each lane owns 4 fixed channels and walks the warp's rows
-      // with coalesced 128-bit accesses (one full 128-byte line per row).  r01 finding 5: epilogue inputs are loaded with
-      // pinned (asm volatile) loads -- with __ldg the compiler sank the scale/shift loads into the row loop.
-      constexpr int CH = 8;                                   // 16-byte chunks per staged 32-column row
-      constexpr int ROWS_PER_IT = 4;
-      constexpr int ITERS = 8;
-      float4* stage = reinterpret_cast<float4*>(smem_stage + (warp - 4) * (32 * 32 * 4));
-      const int row = q * 32 + lane;
-      const int rows_img = p.th * p.tw;
-      const int dn = row / rows_img, rem = row % rows_img;
-      const int dh = rem / p.tw, dw = rem % p.tw;
-      const int n = t.n0 + dn, h = t.h0 + dh, w = t.w0 + dw;
-      const bool valid = (row < p.tn * rows_img) && n < p.nimg && h < p.ho && w < p.wo;
-      const int cg = lane & (CH - 1);                         // column group of this lane
-      const int rsub = lane >> 3;
-      if (t.slot >= 0) {
-        // split tile: plain partial sums in the tile-local [128][BN] workspace layout; the epilogue runs in tail_reduce_kernel
-        float* const wbase = p.ws + ((size_t)t.slot * p.splits + t.z) * (size_t)(BLOCK_M * BN) + (size_t)(q * 32) * BN + col0;
-#pragma unroll
-        for (int pass = 0; pass < W / 32; ++pass) {
-          __syncwarp();
-#pragma unroll
-          for (int j = 0; j < CH; ++j) {
-            const int a0 = pass * 32 + 4 * j;
-            stage[lane * CH + ((j ^ lane) & (CH - 1))] = make_float4(acc[a0], acc[a0 + 1], acc[a0 + 2], acc[a0 + 3]);
-          }
-          __syncwarp();
-#pragma unroll
-          for (int it = 0; it < ITERS; ++it) {
-            const int r = it * ROWS_PER_IT + rsub;
-            *reinterpret_cast<float4*>(wbase + (size_t)r * BN + pass * 32 + cg * 4) = stage[r * CH + ((cg ^ r) & (CH - 1))];
-          }
-        }
-        continue;
-      }
-      const int my_pix = valid ? (int)(((long long)n * p.ho + h) * p.wo + w) : -1;
-      const bool vec_ok = (p.cout & 3) == 0;
-      float* const obase = p.out;
-      const float* const rbase = p.residual;
-      const float* const scale = p.scale;
-      const float* const shift = p.shift;
-      const int act = p.act;
-      int pixr[ITERS];
-#pragma unroll
-      for (int it = 0; it < ITERS; ++it) pixr[it] = __shfl_sync(0xffffffffu, my_pix, it * ROWS_PER_IT + rsub);
-#pragma unroll
-      for (int pass = 0; pass < W / 32; ++pass) {
-        const int c = t.nblk * BN + col0 + pass * 32 + cg * 4;   // first of this lane's 4 output channels in this pass
-        const bool col_ok = c < p.cout;
-        float sc[4] = {1.f, 1.f, 1.f, 1.f}, sh[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int e = 0; e < 4; ++e)
-          if (c + e < p.cout) {
-            if (scale) sc[e] = ld_nc_f32_pinned(scale + c + e);
-            if (shift) sh[e] = ld_nc_f32_pinned(shift + c + e);
-          }
-        float4 rv[ITERS];
-        const bool res_vec = rbase && vec_ok;
-        if (res_vec) {
-#pragma unroll
-          for (int it = 0; it < ITERS; ++it)
-            rv[it] = (pixr[it] >= 0 && col_ok) ? ld_nc_f4_pinned(rbase + (size_t)pixr[it] * p.cout + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        __syncwarp();                                           // previous pass's reads are done
-#pragma unroll
-        for (int j = 0; j < CH; ++j) {
-          const int a0 = pass * 32 + 4 * j;
-          stage[lane * CH + ((j ^ lane) & (CH - 1))] = make_float4(acc[a0], acc[a0 + 1], acc[a0 + 2], acc[a0 + 3]);
-        }
-        __syncwarp();
-#pragma unroll
-        for (int it = 0; it < ITERS; ++it) {
-          if (pixr[it] < 0 || !col_ok) continue;
-          const int r = it * ROWS_PER_IT + rsub;
-          const float4 v = stage[r * CH + ((cg ^ r) & (CH - 1))];
-          float y[4] = {v.x, v.y, v.z, v.w};
-          float res[4] = {0.f, 0.f, 0.f, 0.f};
-          if (res_vec) { res[0] = rv[it].x; res[1] = rv[it].y; res[2] = rv[it].z; res[3] = rv[it].w; }
-          float* optr = obase + (size_t)pixr[it] * p.cout + c;
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            float a = y[e];
-            if (scale) a = __fmul_rn(a, sc[e]);
-            if (shift) a = __fadd_rn(a, sh[e]);
-            if (res_vec) a = __fadd_rn(a, res[e]);
-            else if (rbase && c + e < p.cout) a = __fadd_rn(a, __ldg(rbase + (size_t)pixr[it] * p.cout + c + e));
-            if (act == FRCNN_ACT_RELU) a = fmaxf(a, 0.f);
-            else if (act == FRCNN_ACT_RELU6) a = fminf(fmaxf(a, 0.f), 6.f);
-            y[e] = a;
-          }
-          if (vec_ok) {
-            *reinterpret_cast<float4*>(optr) = make_float4(y[0], y[1], y[2], y[3]);
-          } else {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) if (c + e < p.cout) optr[e] = y[e];
-          }
-        }
-      }
+      epilogue_tile<BN>(p, t, acc, smem_stage, warp - 4, q, lane);
       if (threadIdx.x == 128) FRCNN_TRACE2(703, 0);
     }
   }
@@ -443,6 +457,271 @@ conv_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   __syncthreads();
   if (warp == 12) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
   if (threadIdx.x == 384) FRCNN_TRACE2(704, 0);
+}
+
+// =====================================================================================================================
+// r02: FP16x3 kernel.  Same math contract as the TF32x3 kernel above (fp32-grade products from a two-term split of both
+// operands, three MMAs per product, chunked fp32 accumulation), re-cut around what r01's ncu source page showed:
+//   (1) a TF32 MMA moves 8 k per instruction, an FP16 MMA 16 k at the same 64 cycles (128x128 tile) -- and fp16 has the
+//       SAME 11-bit significand as tf32.  With x_hi = RN_f16(x), x_lo = RN_f16((x - x_hi) * 2^11) every operand is carried
+//       to 2^-22 relative exactly like the tf32 hi/lo pair, at half the tensor time and half the B bytes (shared memory,
+//       L2).  Range: the lo planes are pre-scaled by 2^11 (D_small is folded back with one fma by 2^-11), weights are
+//       pre-scaled per layer by a power of two so that max|w| sits in [2^13, 2^14) (undone exactly by `out_mult` in the
+//       epilogue), activations are converted with saturation (|x| <= 65504; anything the nets here produce is orders of
+//       magnitude below).  Tiny values lose nothing: |x| < 2^-14 still resolves to 2^-35 absolute through the lo plane.
+//   (2) the operand splitter was issue bound: ONE warp per TMEM lane quarter, 334 instructions per k-block at the 0.5 IPC a
+//       single warp gets from the fma/alu pipes = ~750 cycles, in series with a ~530-cycle wait for its TMA box.  Now two
+//       splitter groups alternate k-blocks (8 warps), the fp16 split is 4 instructions per element instead of 5 on twice
+//       the lanes per register, A and B have their own producer warps and 6-deep rings, so the A prefetch no longer queues
+//       behind the B slot's MMA completion.
+//   (3) the chunk accumulator D_main is double buffered: the MMA warp fills D_main[c & 1] while the epilogue warps drain
+//       D_main[(c - 1) & 1] (tcgen05.ld reads 64 B/clk: ~1000 cycles per 128x128 fp32 tile, formerly a stall per chunk).
+//   (4) setmaxnreg moves registers from the producer / MMA / splitter warps to the 8 accumulate+epilogue warps (no spills).
+// Warp roles (640 threads = 5 warpgroups, 1 CTA/SM):
+//   warps 0-3   splitter group 0 (even k-blocks)   wait a_full[sa]; smem row -> fp16 hi/lo pairs; arrive a_empty[sa];
+//   warps 4-7   splitter group 1 (odd k-blocks)    wait ta_empty[st]; tcgen05.st 32 columns; arrive ta_full[st]
+//   warps 8-15  accumulate + epilogue (two per TMEM lane quarter, half the columns each)
+//   warp 16     TMA producer A: wait a_empty[sa] -> 4-D box -> a_full[sa] (tx)
+//   warp 17     TMA producer B: wait b_empty[sb] -> hi + lo weight tiles -> b_full[sb] (tx); never waits for the previous kernel
+//   warp 18     MMA issuer: wait ta_full[st], b_full[sb]; 2 k-slices x 3 tcgen05.mma.kind::f16 (TS); commit -> ta_empty, b_empty;
+//               per chunk: wait acc_empty[b] first, commit -> acc_full[b] last; per unit: wait small_empty first
+//   warp 19     idle (completes the warpgroup for setmaxnreg)
+// TMEM map (512 columns): [0,128) D_main[0] | [128,256) D_main[1] | [256,384) D_small | [384,512) A ring: slot s = 16 columns
+// of hi pairs + 16 columns of lo pairs.
+constexpr int F_THREADS = 640;
+constexpr int F_SA = 6;                                 // smem ring of raw fp32 A tiles
+constexpr int F_SB = 6;                                 // smem ring of B (hi | lo) fp16 tiles
+constexpr int F_ST = 4;                                 // TMEM ring of split A tiles
+constexpr int F_TMEM_DSMALL = 256, F_TMEM_A0 = 384;
+constexpr int F_REGS_SPLIT = 80, F_REGS_EPI = 136, F_REGS_CTRL = 40;
+template <int BN> constexpr int f_b_tile_bytes() { return BN * BLOCK_K * 2; }          // one fp16 plane [BN][32]
+template <int BN> constexpr int f_smem_bytes() {
+  return F_SA * A_TILE_BYTES + F_SB * 2 * f_b_tile_bytes<BN>() + STAGE_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
+}
+
+// K-major, SWIZZLE_64B shared-memory matrix descriptor: rows of 64 B (32 fp16), 8-row groups 512 B apart
+__device__ __forceinline__ uint64_t sw64_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;                  // LBO: unused for swizzled K-major
+  d |= (uint64_t)(512u >> 4) << 32;        // SBO
+  d |= (uint64_t)1 << 46;                  // descriptor version (sm_100)
+  d |= (uint64_t)4 << 61;                  // SWIZZLE_64B
+  return d;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(F_THREADS, 1)
+conv_gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
+                       const __grid_constant__ CUtensorMap tmBlo, const ConvKernelParams p) {
+  constexpr int kBTile = f_b_tile_bytes<BN>();
+  constexpr int kBStage = 2 * kBTile;
+  // instruction descriptor: D = f32 (bits 4-5 = 1), A = B = f16 (format 0), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+  constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+  static_assert(BN <= 128, "accumulators are 128 columns apart");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;                               // F_SA x 16 KiB raw fp32 A tiles (TMA, SWIZZLE_128B)
+  uint8_t* smem_b = smem + F_SA * A_TILE_BYTES;         // F_SB x (B_hi | B_lo) fp16 tiles (TMA, SWIZZLE_64B)
+  uint8_t* smem_stage = smem_b + F_SB * kBStage;        // epilogue transposition buffer
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem_stage + STAGE_BYTES);
+  uint64_t* a_empty = a_full + F_SA;
+  uint64_t* b_full = a_empty + F_SA;
+  uint64_t* b_empty = b_full + F_SB;
+  uint64_t* ta_full = b_empty + F_SB;         // the 128 threads of a splitter group stored hi/lo into the TMEM slot
+  uint64_t* ta_empty = ta_full + F_ST;        // the MMAs reading the TMEM slot completed (tcgen05.commit)
+  uint64_t* acc_full = ta_empty + F_ST;       // [2] D_main[b] holds a finished chunk partial (tcgen05.commit)
+  uint64_t* acc_empty = acc_full + 2;         // [2] the epilogue warps have read D_main[b] (256 arrivals)
+  uint64_t* small_empty = acc_empty + 2;      // the epilogue warps have read D_small of the finished unit (256 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(small_empty + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_kb_total = p.kh * p.kw * (p.cin / BLOCK_K);
+
+  if (warp == 16 && lane == 0) {
+    tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmBhi); tma_prefetch_desc(&tmBlo);
+    for (int s = 0; s < F_SA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], SPLIT_THREADS); }
+    for (int s = 0; s < F_SB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    for (int s = 0; s < F_ST; ++s) { mbar_init(&ta_full[s], SPLIT_THREADS); mbar_init(&ta_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], EPI_THREADS); }
+    mbar_init(small_empty, EPI_THREADS);
+    mbar_fence_init();
+  }
+  if (warp == 18) { tmem_alloc(tmem_slot, TMEM_COLS); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+
+  if (warp < 8) {
+    // ---------------- operand splitter: raw fp32 row in smem -> fp16 (hi, lo * 2^11) pairs in the TMEM A ring ----------------
+    reg_dec<F_REGS_SPLIT>();
+    const int g = warp >> 2;                  // group: handles running k-blocks kbt == g (mod 2)
+    const int q = warp & 3;                   // TMEM lane quarter
+    const int row = q * 32 + lane;
+    const uint32_t lane_field = (uint32_t)(q * 32) << 16;
+    int total_kb = 0;                         // k-blocks of all units of this CTA (the splitter needs nothing else about them)
+    for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) total_kb += decode_unit(p, u, num_kb_total).num_kb;
+    int sa = g; uint32_t pa = 0;
+#pragma unroll 1
+    for (int kbt = g; kbt < total_kb; kbt += 2) {
+      MBAR_WAIT(&a_full[sa], pa, 1, kbt);
+      // SWIZZLE_128B: 16-byte chunk c of row r sits at chunk (c ^ (r & 7)); quarter-warp phases are conflict-free
+      const uint8_t* arow = smem_a + sa * A_TILE_BYTES + row * 128;
+      uint32_t pk[32];                        // [0,16): hi pairs (k, k+1), [16,32): lo pairs
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const float4 v = *reinterpret_cast<const float4*>(arow + ((c ^ (row & 7)) << 4));
+        const uint32_t h01 = pack_f16x2_sat(v.x, v.y), h23 = pack_f16x2_sat(v.z, v.w);
+        const float2 f01 = __half22float2(*reinterpret_cast<const __half2*>(&h01));
+        const float2 f23 = __half22float2(*reinterpret_cast<const __half2*>(&h23));
+        pk[2 * c] = h01; pk[2 * c + 1] = h23;
+        pk[16 + 2 * c] = pack_f16x2_sat(__fmul_rn(__fsub_rn(v.x, f01.x), 2048.f), __fmul_rn(__fsub_rn(v.y, f01.y), 2048.f));
+        pk[16 + 2 * c + 1] = pack_f16x2_sat(__fmul_rn(__fsub_rn(v.z, f23.x), 2048.f), __fmul_rn(__fsub_rn(v.w, f23.y), 2048.f));
+      }
+      // raw tile consumed: the arrive carries a data dependency on every one of the 8 row loads, so it cannot be issued
+      // while a load is still outstanding (the A producer re-fills the slot as soon as all 128 threads arrived)
+      mbar_arrive_after(&a_empty[sa], (pk[0] | pk[2] | pk[4]) | (pk[6] | pk[8] | pk[10]) | (pk[12] | pk[14]));
+      const int st = kbt & (F_ST - 1);
+      MBAR_WAIT(&ta_empty[st], (((uint32_t)kbt >> 2) & 1u) ^ 1u, 2, kbt);   // TMEM slot no longer read by the tensor core
+      tc_fence_after();
+      tmem_st_32x32(tmem_base + lane_field + (uint32_t)(F_TMEM_A0 + st * 32), pk);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&ta_full[st]);
+      sa += 2; if (sa >= F_SA) { sa -= F_SA; pa ^= 1u; }
+    }
+  } else if (warp < 16) {
+    // ---------------- accumulate (TMEM chunk partials -> fp32 registers, RN adds) + epilogue ----------------
+    reg_inc<F_REGS_EPI>();
+    constexpr int W = BN / 2;                 // columns owned by this warp (two warps share a TMEM lane quarter)
+    const int q = warp & 3;                   // TMEM lane quarter this warp may access
+    const int ew = warp - 8;
+    const int col0 = (ew >> 2) * W;
+    const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col0;
+    pdl_wait();                               // residual / output buffers belong to earlier kernels until they completed
+    uint32_t ct = 0;
+    for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
+      const Unit t = decode_unit(p, u, num_kb_total);
+      const int num_chunks = (t.num_kb + p.kb_per_chunk - 1) / p.kb_per_chunk;
+      float acc[W];
+#pragma unroll
+      for (int j = 0; j < W; ++j) acc[j] = 0.f;
+      for (int c = 0; c < num_chunks; ++c, ++ct) {
+        const uint32_t b = ct & 1u;
+        MBAR_WAIT(&acc_full[b], (ct >> 1) & 1u, 3, ct);
+        tc_fence_after();
+#pragma unroll
+        for (int c0 = 0; c0 < W; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(tq + b * 128u + (uint32_t)c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[c0 + j] = __fadd_rn(acc[c0 + j], __uint_as_float(v[j]));
+        }
+        if (c + 1 == num_chunks) {
+          // the cross terms of the unit's whole k range (complete: this acc_full commit covered every MMA), scaled by 2^11
+#pragma unroll
+          for (int c0 = 0; c0 < W; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld_32x32(tq + (uint32_t)(F_TMEM_DSMALL + c0), v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[c0 + j] = __fmaf_rn(__uint_as_float(v[j]), 0.00048828125f, acc[c0 + j]);
+          }
+          tc_fence_before();
+          mbar_arrive(small_empty);           // the next unit's first MMA may overwrite D_small
+        }
+        tc_fence_before();
+        mbar_arrive(&acc_empty[b]);           // the MMA warp may overwrite D_main[b]
+      }
+      epilogue_tile<BN>(p, t, acc, smem_stage, ew, q, lane);
+    }
+  } else {
+    reg_dec<F_REGS_CTRL>();
+    if (warp == 16 && lane == 0) {
+      // ---------------- TMA producer, activations ----------------
+      const int cchunks = p.cin / BLOCK_K;
+      pdl_wait();                             // the input belongs to the previous kernel until it completed
+      int sa = 0; uint32_t pa = 0;
+      for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
+        const Unit t = decode_unit(p, u, num_kb_total);
+#pragma unroll 1
+        for (int kb = 0; kb < t.num_kb; ++kb) {
+          const int gk = t.kb0 + kb;                              // global k-block -> (filter tap, channel chunk)
+          const int tap = gk / cchunks, kc = gk - tap * cchunks;
+          const int r = tap / p.kw, s = tap - r * p.kw;
+          MBAR_WAIT(&a_empty[sa], pa ^ 1u, 4, kb);                       // a splitter group has consumed the raw tile
+          mbar_expect_tx(&a_full[sa], (uint32_t)p.a_box_bytes);
+          tma_load_4d(smem_a + sa * A_TILE_BYTES, &tmA, &a_full[sa], kc * BLOCK_K, t.w0 * p.stride + s - p.pad_l,
+                      t.h0 * p.stride + r - p.pad_t, t.n0);
+          if (++sa == F_SA) { sa = 0; pa ^= 1u; }
+        }
+      }
+    } else if (warp == 17 && lane == 0) {
+      // ---------------- TMA producer, weights (static data: runs ahead of the previous kernel's tail) ----------------
+      int sb = 0; uint32_t pb = 0;
+      for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
+        const Unit t = decode_unit(p, u, num_kb_total);
+#pragma unroll 1
+        for (int kb = 0; kb < t.num_kb; ++kb) {
+          const int kcoord = (t.kb0 + kb) * BLOCK_K;              // K axis of the packed weights = (tap, cin) flattened
+          MBAR_WAIT(&b_empty[sb], pb ^ 1u, 5, kb);                       // the MMAs that read this slot completed
+          mbar_expect_tx(&b_full[sb], (uint32_t)kBStage);
+          tma_load_2d(smem_b + sb * kBStage, &tmBhi, &b_full[sb], kcoord, t.nblk * BN);
+          tma_load_2d(smem_b + sb * kBStage + kBTile, &tmBlo, &b_full[sb], kcoord, t.nblk * BN);
+          if (++sb == F_SB) { sb = 0; pb ^= 1u; }
+        }
+      }
+    } else if (warp == 18 && lane == 0) {
+      // ---------------- MMA issuer ----------------
+      uint32_t kbt = 0, ct = 0, ut = 0;
+      int sb = 0; uint32_t pb = 0;
+      const uint32_t d_small = tmem_base + (uint32_t)F_TMEM_DSMALL;
+      for (int u = blockIdx.x; u < p.total_units; u += gridDim.x, ++ut) {
+        const Unit t = decode_unit(p, u, num_kb_total);
+        int in_chunk = 0;
+#pragma unroll 1
+        for (int kb = 0; kb < t.num_kb; ++kb, ++kbt) {
+          const uint32_t b = ct & 1u;
+          if (in_chunk == 0) MBAR_WAIT(&acc_empty[b], ((ct >> 1) & 1u) ^ 1u, 6, kbt);   // D_main[b]'s previous chunk has been drained
+          if (kb == 0) MBAR_WAIT(small_empty, (ut & 1u) ^ 1u, 7, kbt);                  // D_small of the previous unit has been read
+          const uint32_t st = kbt & (uint32_t)(F_ST - 1);
+          MBAR_WAIT(&ta_full[st], (kbt >> 2) & 1u, 8, kbt);
+          MBAR_WAIT(&b_full[sb], pb, 9, kbt);
+          tc_fence_after();
+          const uint32_t sbase = smem_u32(smem_b + sb * kBStage);
+          const uint64_t b_hi = sw64_desc(sbase);
+          const uint64_t b_lo = sw64_desc(sbase + kBTile);
+          const uint32_t a_hi = tmem_base + (uint32_t)F_TMEM_A0 + st * 32u;
+          const uint32_t a_lo = a_hi + 16u;
+          const uint32_t d_main = tmem_base + b * 128u;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / 16; ++k) {
+            const uint64_t off = (uint64_t)(k * 16 * 2) >> 4;  // B: advance 16 fp16 = 32 B inside the swizzle row
+            const uint32_t ak = (uint32_t)(k * 8);             // A: 16 fp16 = 8 TMEM columns
+            umma_f16_ts(d_small, a_lo + ak, b_hi + off, kIdesc, (k > 0 || kb > 0) ? 1u : 0u);
+            umma_f16_ts(d_small, a_hi + ak, b_lo + off, kIdesc, 1u);
+            umma_f16_ts(d_main, a_hi + ak, b_hi + off, kIdesc, (k > 0 || in_chunk > 0) ? 1u : 0u);
+          }
+          umma_commit(&ta_empty[st]);
+          umma_commit(&b_empty[sb]);
+          if (++in_chunk == p.kb_per_chunk || kb + 1 == t.num_kb) {
+            umma_commit(&acc_full[b]);
+            in_chunk = 0; ++ct;
+          }
+          if (++sb == F_SB) { sb = 0; pb ^= 1u; }
+        }
+      }
+    }
+    __syncwarp();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 18) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
 }
 
 // Second pass for split tiles: out = act((sum_z ws[slot][z]) * scale + shift (+ residual)), z summed in index order
@@ -525,14 +804,15 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 static int encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                      const uint32_t* box, const uint32_t* estr) {
+                      const uint32_t* box, const uint32_t* estr, CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                      CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return ERR_DRIVER_ENTRY; }
   cuuint64_t gd[5]; cuuint64_t gs[4]; cuuint32_t bx[5]; cuuint32_t es[5];
   for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = estr[i]; }
   for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+  CUresult r = fn(m, dtype, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (CUresult %d) rank=%d dims=[%llu,%llu,%llu,%llu] box=[%u,%u,%u,%u]", (int)r, rank,
@@ -551,6 +831,7 @@ struct frcnn_conv_plan {
   CUtensorMap tmA, tmBhi, tmBlo;
   ConvKernelParams kp;
   int block_n, stages, smem;
+  int impl;                // FRCNN_CONV_F16X3 | FRCNN_CONV_TF32X3
   dim3 grid;
   int n_tail;
   float* ws;               // owned workspace of the split tiles
@@ -609,6 +890,30 @@ static int launch(const frcnn_conv_plan* p, cudaStream_t st) {
   return OK;
 }
 
+template <int BN>
+static int launch_f16(const frcnn_conv_plan* p, cudaStream_t st) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    FRCNN_CUDA(cudaFuncSetAttribute(conv_gemm_f16x3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, f_smem_bytes<BN>()));
+    attr_done = true;
+  }
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  const bool pdl = pdl_enabled();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = p->grid; cfg.blockDim = dim3(F_THREADS); cfg.dynamicSmemBytes = f_smem_bytes<BN>(); cfg.stream = st;
+  cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+  FRCNN_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_f16x3_kernel<BN>, p->tmA, p->tmBhi, p->tmBlo, p->kp));
+  if (p->n_tail > 0) {
+    cudaLaunchConfig_t rc{};
+    rc.gridDim = dim3((unsigned)(p->n_tail * (BLOCK_M / (256 / (BN / 4))))); rc.blockDim = dim3(256); rc.dynamicSmemBytes = 0; rc.stream = st;
+    rc.attrs = attr; rc.numAttrs = pdl ? 1 : 0;
+    FRCNN_CUDA(cudaLaunchKernelEx(&rc, tail_reduce_kernel<BN>, p->kp));
+  }
+  return OK;
+}
+
 // Host-side work decomposition of one layer (no CUDA calls: unit-testable on a CPU box through frcnn_conv_plan_geometry).
 struct Geometry {
   int n, h, w, ho, wo;           // after flattening 1x1/stride-1 layers to one row of n*h*w pixels
@@ -635,6 +940,7 @@ static int decide_geometry(const frcnn_conv_desc* d, int sms, Geometry* g) {
   g->tiles_w = cdiv(g->wo, g->tw); g->tiles_h = cdiv(g->ho, g->th); g->tiles_n = cdiv(g->n, g->tn);
   g->m_tiles = (long)g->tiles_w * g->tiles_h * g->tiles_n;
   g->num_kb = d->kh * d->kw * d->cin / BLOCK_K;
+  const bool f16 = d->impl != FRCNN_CONV_TF32X3;
   g->kpc = d->kb_per_chunk > 0 ? d->kb_per_chunk : 8;
   int bn = d->block_n;
   if (bn == 0) {
@@ -647,7 +953,7 @@ static int decide_geometry(const frcnn_conv_desc* d, int sms, Geometry* g) {
       const long waves = (ctas + sms - 1) / sms;
       // measured (profiles/r01): a k-block costs about the same whatever block_n is (the 128-row A operand dominates for
       // N <= 128), plus a fixed per-unit cost => fewest rounds wins, widest tile on ties
-      const long cost = waves * (g->num_kb * 1400L + 6000L);
+      const long cost = f16 ? waves * (g->num_kb * 500L + 4000L) : waves * (g->num_kb * 1400L + 6000L);
       if (best < 0 || cost < best) { best = cost; bn = c; }
     }
   }
@@ -714,14 +1020,17 @@ extern "C" int frcnn_conv_plan_create(frcnn_conv_plan** out, const frcnn_conv_de
     int rc = encode_map(&p->tmA, d->in_dev, 4, dims, strides, box, es);
     if (rc) { free(p); return rc; }
   }
+  const bool f16 = d->impl != FRCNN_CONV_TF32X3;
   {
     const uint64_t ktot = (uint64_t)d->kh * d->kw * d->cin;
     uint64_t dims[2] = {ktot, (uint64_t)d->cout};
-    uint64_t strides[1] = {ktot * 4};
+    uint64_t strides[1] = {ktot * (f16 ? 2 : 4)};
     uint32_t box[2] = {(uint32_t)BLOCK_K, (uint32_t)bn};
     uint32_t es[2] = {1, 1};
-    int rc = encode_map(&p->tmBhi, d->w_hi_dev, 2, dims, strides, box, es);
-    if (!rc) rc = encode_map(&p->tmBlo, d->w_lo_dev, 2, dims, strides, box, es);
+    const CUtensorMapDataType dt = f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    const CUtensorMapSwizzle sw = f16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+    int rc = encode_map(&p->tmBhi, d->w_hi_dev, 2, dims, strides, box, es, dt, sw);
+    if (!rc) rc = encode_map(&p->tmBlo, d->w_lo_dev, 2, dims, strides, box, es, dt, sw);
     if (rc) { free(p); return rc; }
   }
   ConvKernelParams& k = p->kp;
@@ -733,6 +1042,7 @@ extern "C" int frcnn_conv_plan_create(frcnn_conv_plan** out, const frcnn_conv_de
   k.a_box_bytes = g.tn * g.th * g.tw * BLOCK_K * 4;
   k.kb_per_chunk = g.kpc;
   k.trace = nullptr;
+  k.out_mult = f16 ? (d->out_mult != 0.f ? d->out_mult : 1.f) : 1.f;
   k.m_tiles = (int)g.m_tiles; k.n_tiles = g.n_tiles;
   k.kb_per_split = g.kbs; k.splits = g.splits; k.n_full = (int)(g.tiles - g.n_tail);
   k.total_units = (int)g.total_units;
@@ -744,8 +1054,9 @@ extern "C" int frcnn_conv_plan_create(frcnn_conv_plan** out, const frcnn_conv_de
   }
   p->grid = dim3((unsigned)g.grid, 1, 1);
   p->block_n = bn;
-  p->stages = RING;
-  p->smem = bn == 128 ? smem_bytes<128>() : smem_bytes<64>();
+  p->impl = f16 ? FRCNN_CONV_F16X3 : FRCNN_CONV_TF32X3;
+  p->stages = f16 ? F_SA : RING;
+  p->smem = f16 ? (bn == 128 ? f_smem_bytes<128>() : f_smem_bytes<64>()) : (bn == 128 ? smem_bytes<128>() : smem_bytes<64>());
   *out = p;
   return OK;
 }
@@ -753,10 +1064,8 @@ extern "C" int frcnn_conv_plan_create(frcnn_conv_plan** out, const frcnn_conv_de
 extern "C" int frcnn_conv_plan_run(const frcnn_conv_plan* p, void* stream) {
   FRCNN_REQUIRE(p, "null plan");
   cudaStream_t st = (cudaStream_t)stream;
-  switch (p->block_n) {
-    case 128: return launch<128>(p, st);
-    default: return launch<64>(p, st);
-  }
+  if (p->impl == FRCNN_CONV_F16X3) return p->block_n == 128 ? launch_f16<128>(p, st) : launch_f16<64>(p, st);
+  return p->block_n == 128 ? launch<128>(p, st) : launch<64>(p, st);
 }
 
 extern "C" int frcnn_conv_plan_info(const frcnn_conv_plan* p, int* block_n, int* tile_n, int* tile_h, int* tile_w,
@@ -771,6 +1080,20 @@ extern "C" int frcnn_conv_plan_info(const frcnn_conv_plan* p, int* block_n, int*
   if (stages) *stages = p->n_tail > 0 ? p->kp.splits : 1;   /* "splits" of the tail tiles */
   if (smem) *smem = p->smem;
   return OK;
+}
+
+extern "C" int frcnn_debug_watchdog(unsigned int* out16, int reset) {
+  FRCNN_REQUIRE(out16, "null argument");
+#ifdef FRCNN_WATCHDOG
+  FRCNN_CUDA(cudaMemcpyFromSymbol(out16, g_watchdog, 16 * sizeof(unsigned int)));
+  if (reset) { unsigned int z[16] = {0}; FRCNN_CUDA(cudaMemcpyToSymbol(g_watchdog, z, sizeof(z))); }
+  return OK;
+#else
+  (void)reset;
+  for (int i = 0; i < 16; ++i) out16[i] = 0;
+  out16[15] = 0xffffffffu;   // "not a watchdog build"
+  return OK;
+#endif
 }
 
 extern "C" int frcnn_conv_plan_set_trace(frcnn_conv_plan* p, long long* trace_dev) {

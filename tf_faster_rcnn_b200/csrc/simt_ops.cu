@@ -1,6 +1,8 @@
 // Bandwidth-bound stages of the TEST graph as coalesced / float4-vectorised SIMT kernels (fp32).
 // Where the oracle (numpy, no FMA) performs separate roundings the kernels use __f*_rn intrinsics so that
 // nvcc cannot contract them; reference file:line citations are in include/frcnn_b200.h.
+#include <cuda_fp16.h>
+#include <math.h>
 #include "common.cuh"
 #include "../../include/frcnn_b200.h"
 
@@ -23,6 +25,20 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, float* __restri
     const float h = to_tf32(v);
     hi[i] = h;
     lo[i] = to_tf32(__fsub_rn(v, h));
+  }
+}
+
+// fp16 planes for the FP16x3 kernel: hi = RN_f16(w * 2^wexp), lo = RN_f16((w * 2^wexp - hi) * 2^11)  (see conv_gemm.cu)
+__global__ void pack_weights_f16_kernel(const float* __restrict__ w, __half* __restrict__ hi, __half* __restrict__ lo,
+                                        int ktot, int cout, float wmul) {
+  const size_t total = (size_t)ktot * cout;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int k = (int)(i % ktot);
+    const int co = (int)(i / ktot);
+    const float v = __fmul_rn(w[(size_t)k * cout + co], wmul);
+    const __half h = __float2half_rn(v);
+    hi[i] = h;
+    lo[i] = __float2half_rn(__fmul_rn(__fsub_rn(v, __half2float(h)), 2048.f));
   }
 }
 
@@ -379,7 +395,21 @@ static inline unsigned blocks_for(long total, int threads) { return (unsigned)((
 
 using namespace frcnn;
 
-extern "C" int frcnn_pack_conv_weights(const float* w, float* hi, float* lo, int kh, int kw, int cin, int cout, void* stream) {
+extern "C" int frcnn_pack_conv_weights(const float* w, void* hi, void* lo, int kh, int kw, int cin, int cout, int wexp, void* stream) {
+  FRCNN_REQUIRE(w && hi && lo && kh > 0 && kw > 0 && cin > 0 && cout > 0, "bad argument");
+  FRCNN_REQUIRE(wexp >= -100 && wexp <= 100, "pack_conv_weights: wexp=%d out of range", wexp);
+  {
+    const int ktot = kh * kw * cin;
+    const long total = (long)ktot * cout;
+    unsigned blocks = blocks_for(total, 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    pack_weights_f16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, (__half*)hi, (__half*)lo, ktot, cout, ldexpf(1.f, wexp));
+    FRCNN_LAUNCH_CHECK();
+    return OK;
+  }
+}
+
+extern "C" int frcnn_pack_conv_weights_tf32(const float* w, float* hi, float* lo, int kh, int kw, int cin, int cout, void* stream) {
   FRCNN_REQUIRE(w && hi && lo && kh > 0 && kw > 0 && cin > 0 && cout > 0, "bad argument");
   const int ktot = kh * kw * cin;
   const long total = (long)ktot * cout;

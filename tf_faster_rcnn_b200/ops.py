@@ -3,6 +3,8 @@
 launches hand-written sm_100a kernels from libfrcnn_b200.so.  No CPU fallbacks.
 """
 import ctypes as C
+import os
+
 import numpy as np
 import torch
 
@@ -29,19 +31,44 @@ def same_pads(n, k, s):
     return total // 2, total - total // 2
 
 
+def conv_impl():
+    """Dense-kernel generation: FP16x3 (default) or the r01 TF32x3 kernel (FRCNN_CONV_IMPL=tf32, A/B measurements)."""
+    return N.CONV_TF32X3 if os.environ.get("FRCNN_CONV_IMPL", "f16") == "tf32" else N.CONV_F16X3
+
+
+def weight_exponent(w):
+    """wexp with max|w| * 2^wexp in [2^13, 2^14): the fp16 hi plane then spans 27 binades below the layer's largest
+    weight before going subnormal (and even those keep 2^-35 * max|w| through the lo plane)."""
+    m = float(np.max(np.abs(w))) if w.size else 0.0
+    if not np.isfinite(m) or m <= 0.0:
+        return 0
+    return int(13 - np.floor(np.log2(m)))
+
+
 class PackedConv:
     """Device-resident K-major hi/lo weight planes + epilogue vectors of one conv / FC layer."""
 
-    def __init__(self, w_hwio, scale=None, shift=None):
-        w = torch.as_tensor(np.ascontiguousarray(w_hwio), dtype=torch.float32).cuda()
+    def __init__(self, w_hwio, scale=None, shift=None, impl=None):
+        wnp = np.ascontiguousarray(w_hwio, dtype=np.float32)
+        w = torch.from_numpy(wnp).cuda()
         if w.dim() == 2:                     # FC [in,out] == 1x1 conv
             w = w.view(1, 1, w.shape[0], w.shape[1])
         self.kh, self.kw, self.cin, self.cout = (int(v) for v in w.shape)
         ktot = self.kh * self.kw * self.cin
-        self.w_hi = torch.empty((self.cout, ktot), dtype=torch.float32, device="cuda")
-        self.w_lo = torch.empty_like(self.w_hi)
-        N.check(N.lib().frcnn_pack_conv_weights(_p(w), _p(self.w_hi), _p(self.w_lo), self.kh, self.kw, self.cin,
-                                                self.cout, _stream()), "pack_conv_weights")
+        self.impl = conv_impl() if impl is None else impl
+        if self.impl == N.CONV_F16X3:
+            self.wexp = weight_exponent(wnp)
+            self.out_mult = float(np.ldexp(1.0, -self.wexp))
+            self.w_hi = torch.empty((self.cout, ktot), dtype=torch.float16, device="cuda")
+            self.w_lo = torch.empty_like(self.w_hi)
+            N.check(N.lib().frcnn_pack_conv_weights(_p(w), _p(self.w_hi), _p(self.w_lo), self.kh, self.kw, self.cin,
+                                                    self.cout, self.wexp, _stream()), "pack_conv_weights")
+        else:
+            self.wexp, self.out_mult = 0, 1.0
+            self.w_hi = torch.empty((self.cout, ktot), dtype=torch.float32, device="cuda")
+            self.w_lo = torch.empty_like(self.w_hi)
+            N.check(N.lib().frcnn_pack_conv_weights_tf32(_p(w), _p(self.w_hi), _p(self.w_lo), self.kh, self.kw, self.cin,
+                                                         self.cout, _stream()), "pack_conv_weights_tf32")
         torch.cuda.current_stream().synchronize()
         self.scale = None if scale is None else torch.as_tensor(np.ascontiguousarray(scale), dtype=torch.float32).cuda()
         self.shift = None if shift is None else torch.as_tensor(np.ascontiguousarray(shift), dtype=torch.float32).cuda()
@@ -57,7 +84,8 @@ class ConvPlan:
         no, ho, wo, co = out.shape
         assert no == n and co == pc.cout
         d = N.ConvDesc(_p(x), _p(pc.w_hi), _p(pc.w_lo), _p(pc.scale), _p(pc.shift), _p(residual), _p(out),
-                       n, h, w, cin, pc.cout, pc.kh, pc.kw, stride, pad_t, pad_l, ho, wo, act, block_n, kb_per_chunk, split_k)
+                       n, h, w, cin, pc.cout, pc.kh, pc.kw, stride, pad_t, pad_l, ho, wo, act, block_n, kb_per_chunk, split_k,
+                       pc.impl, pc.out_mult)
         self._h = C.c_void_p()
         N.check(N.lib().frcnn_conv_plan_create(C.byref(self._h), C.byref(d)), "conv_plan_create")
         self._keep = (x, pc, out, residual)
