@@ -77,6 +77,9 @@ struct ConvKernelParams {
   int m_tiles, n_tiles, total_units, n_full, splits;
   float* ws;
   long long* trace;   // debug: clock64() stamps of CTA (0,0)'s pipeline hand-offs; normally NULL
+  int num_kb_total;   // f16x3: 64-wide k-blocks of the whole K loop
+  int dbg;            // development ablations (FRCNN_CONV_DBG, read at plan creation): 1 splitter skips load+convert, 2 MMA issues only
+                      // the hi*hi product, 4 / 8 producer A / B skip their TMA, 16 epilogue skips the chunk promotion loads.  0 in production.
   float out_mult;     // f16x3: 2^-wexp, undoes the power-of-two weight scaling (exact); tf32x3: 1
 };
 
@@ -461,7 +464,7 @@ conv_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
 
 // =====================================================================================================================
 // r02: FP16x3 kernel.  Same math contract as the TF32x3 kernel above (fp32-grade products from a two-term split of both
-// operands, three MMAs per product, chunked fp32 accumulation), re-cut around what r01's ncu source page showed:
+// operands, three MMAs per product, chunked fp32 accumulation), re-cut around what the ncu source pages showed:
 //   (1) a TF32 MMA moves 8 k per instruction, an FP16 MMA 16 k at the same 64 cycles (128x128 tile) -- and fp16 has the
 //       SAME 11-bit significand as tf32.  With x_hi = RN_f16(x), x_lo = RN_f16((x - x_hi) * 2^11) every operand is carried
 //       to 2^-22 relative exactly like the tf32 hi/lo pair, at half the tensor time and half the B bytes (shared memory,
@@ -469,45 +472,40 @@ conv_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
 //       pre-scaled per layer by a power of two so that max|w| sits in [2^13, 2^14) (undone exactly by `out_mult` in the
 //       epilogue), activations are converted with saturation (|x| <= 65504; anything the nets here produce is orders of
 //       magnitude below).  Tiny values lose nothing: |x| < 2^-14 still resolves to 2^-35 absolute through the lo plane.
-//   (2) the operand splitter was issue bound: ONE warp per TMEM lane quarter, 334 instructions per k-block at the 0.5 IPC a
-//       single warp gets from the fma/alu pipes = ~750 cycles, in series with a ~530-cycle wait for its TMA box.  Now two
-//       splitter groups alternate k-blocks (8 warps), the fp16 split is 4 instructions per element instead of 5 on twice
-//       the lanes per register, A and B have their own producer warps and 6-deep rings, so the A prefetch no longer queues
-//       behind the B slot's MMA completion.
-//   (3) the chunk accumulator D_main is double buffered: the MMA warp fills D_main[c & 1] while the epilogue warps drain
-//       D_main[(c - 1) & 1] (tcgen05.ld reads 64 B/clk: ~1000 cycles per 128x128 fp32 tile, formerly a stall per chunk).
-//   (4) setmaxnreg moves registers from the producer / MMA / splitter warps to the 8 accumulate+epilogue warps (no spills).
+//   (2) r01's operand splitter was issue bound: ONE warp per TMEM lane quarter, 334 instructions per k-block at the 0.5 IPC a
+//       single warp gets from the fma/alu pipes.  Now 8 splitter warps (group g converts the g-th 32-channel half of every
+//       64-wide k-block), 4 instructions per element on packed pairs, and A / B have their own producer warps and rings.
+//   (3) r02 finding 1+2: the single MMA-issuing thread is a serial instruction stream at ~5 cycles per instruction (no other
+//       warp hides its latencies).  Inside `if (lane == 0)` ptxas wrapped every UTCHMMA in an ELECT / R2UR.BROADCAST /
+//       BRA.U.ANY loop (~150 instructions per 32-wide k-block = 1050 cycles); with the whole warp converged and elect.sync
+//       only around the tcgen05 instructions it was still 114 instructions = 600 cycles per 32 k (tensor floor: 384).  Hence
+//       k-blocks of 64: 12 MMAs, 2 waits and 2-3 commits per loop trip halve the per-k issue cost.
+//   (4) the chunk accumulator D_main is double buffered: the MMA warp fills D_main[c & 1] while the epilogue warps drain
+//       D_main[(c - 1) & 1] (tcgen05.ld reads ~64 B/clk: ~1000 cycles per 128x128 fp32 tile, formerly a stall per chunk).
+//   (5) setmaxnreg moves registers from the producer / MMA / splitter warps to the 8 accumulate+epilogue warps (no spills).
 // Warp roles (640 threads = 5 warpgroups, 1 CTA/SM):
-//   warps 0-3   splitter group 0 (even k-blocks)   wait a_full[sa]; smem row -> fp16 hi/lo pairs; arrive a_empty[sa];
-//   warps 4-7   splitter group 1 (odd k-blocks)    wait ta_empty[st]; tcgen05.st 32 columns; arrive ta_full[st]
+//   warps 0-3   splitter group 0 (channels  0..31 of the k-block)  wait a_full[sa]; smem row -> fp16 hi/lo pairs; arrive a_empty[sa];
+//   warps 4-7   splitter group 1 (channels 32..63)                 wait ta_empty[st]; tcgen05.st 32 columns; arrive ta_full[st]
 //   warps 8-15  accumulate + epilogue (two per TMEM lane quarter, half the columns each)
-//   warp 16     TMA producer A: wait a_empty[sa] -> 4-D box -> a_full[sa] (tx)
+//   warp 16     TMA producer A: wait a_empty[sa] -> two 4-D boxes (one per 32-channel half: each its own filter tap) -> a_full[sa] (tx)
 //   warp 17     TMA producer B: wait b_empty[sb] -> hi + lo weight tiles -> b_full[sb] (tx); never waits for the previous kernel
-//   warp 18     MMA issuer: wait ta_full[st], b_full[sb]; 2 k-slices x 3 tcgen05.mma.kind::f16 (TS); commit -> ta_empty, b_empty;
+//   warp 18     MMA issuer: wait ta_full[st], b_full[sb]; 4 k-slices x 3 tcgen05.mma.kind::f16 (TS); commit -> ta_empty, b_empty;
 //               per chunk: wait acc_empty[b] first, commit -> acc_full[b] last; per unit: wait small_empty first
 //   warp 19     idle (completes the warpgroup for setmaxnreg)
-// TMEM map (512 columns): [0,128) D_main[0] | [128,256) D_main[1] | [256,384) D_small | [384,512) A ring: slot s = 16 columns
-// of hi pairs + 16 columns of lo pairs.
+// TMEM map (512 columns): [0,128) D_main[0] | [128,256) D_main[1] | [256,384) D_small | [384,512) A ring: slot s = 64 columns =
+// (hi pairs | lo pairs) of channels 0..31, then of channels 32..63.
 constexpr int F_THREADS = 640;
-constexpr int F_SA = 6;                                 // smem ring of raw fp32 A tiles
-constexpr int F_SB = 6;                                 // smem ring of B (hi | lo) fp16 tiles
-constexpr int F_ST = 4;                                 // TMEM ring of split A tiles
+constexpr int F_BK = 64;                                // channels per k-block (two 32-channel TMA boxes)
+constexpr int F_SA = 3;                                 // smem ring of raw fp32 A stages (2 x 16 KiB each)
+constexpr int F_SB = 3;                                 // smem ring of B (hi | lo) fp16 stages
+constexpr int F_ST = 2;                                 // TMEM ring of split A tiles
+constexpr int F_A_STAGE = 2 * A_TILE_BYTES;
 constexpr int F_TMEM_DSMALL = 256, F_TMEM_A0 = 384;
 constexpr int F_REGS_SPLIT = 80, F_REGS_EPI = 136, F_REGS_CTRL = 40;
-template <int BN> constexpr int f_b_tile_bytes() { return BN * BLOCK_K * 2; }          // one fp16 plane [BN][32]
+constexpr int F_SPLIT_THREADS = 256;
+template <int BN> constexpr int f_b_tile_bytes() { return BN * F_BK * 2; }          // one fp16 plane [BN][64]: 128-byte rows
 template <int BN> constexpr int f_smem_bytes() {
-  return F_SA * A_TILE_BYTES + F_SB * 2 * f_b_tile_bytes<BN>() + STAGE_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
-}
-
-// K-major, SWIZZLE_64B shared-memory matrix descriptor: rows of 64 B (32 fp16), 8-row groups 512 B apart
-__device__ __forceinline__ uint64_t sw64_desc(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)1 << 16;                  // LBO: unused for swizzled K-major
-  d |= (uint64_t)(512u >> 4) << 32;        // SBO
-  d |= (uint64_t)1 << 46;                  // descriptor version (sm_100)
-  d |= (uint64_t)4 << 61;                  // SWIZZLE_64B
-  return d;
+  return F_SA * F_A_STAGE + F_SB * 2 * f_b_tile_bytes<BN>() + STAGE_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
 }
 
 template <int BN>
@@ -522,14 +520,14 @@ conv_gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* smem_a = smem;                               // F_SA x 16 KiB raw fp32 A tiles (TMA, SWIZZLE_128B)
-  uint8_t* smem_b = smem + F_SA * A_TILE_BYTES;         // F_SB x (B_hi | B_lo) fp16 tiles (TMA, SWIZZLE_64B)
+  uint8_t* smem_a = smem;                               // F_SA x 2 x 16 KiB raw fp32 A tiles (TMA, SWIZZLE_128B)
+  uint8_t* smem_b = smem + F_SA * F_A_STAGE;            // F_SB x (B_hi | B_lo) fp16 tiles (TMA, SWIZZLE_128B)
   uint8_t* smem_stage = smem_b + F_SB * kBStage;        // epilogue transposition buffer
   uint64_t* a_full = reinterpret_cast<uint64_t*>(smem_stage + STAGE_BYTES);
   uint64_t* a_empty = a_full + F_SA;
   uint64_t* b_full = a_empty + F_SA;
   uint64_t* b_empty = b_full + F_SB;
-  uint64_t* ta_full = b_empty + F_SB;         // the 128 threads of a splitter group stored hi/lo into the TMEM slot
+  uint64_t* ta_full = b_empty + F_SB;         // both splitter groups (256 threads) stored their halves into the TMEM slot
   uint64_t* ta_empty = ta_full + F_ST;        // the MMAs reading the TMEM slot completed (tcgen05.commit)
   uint64_t* acc_full = ta_empty + F_ST;       // [2] D_main[b] holds a finished chunk partial (tcgen05.commit)
   uint64_t* acc_empty = acc_full + 2;         // [2] the epilogue warps have read D_main[b] (256 arrivals)
@@ -538,13 +536,13 @@ conv_gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_kb_total = p.kh * p.kw * (p.cin / BLOCK_K);
+  const int num_kb_total = p.num_kb_total;    // 64-wide k-blocks of the whole K loop (the last may be half empty)
 
   if (warp == 16 && lane == 0) {
     tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmBhi); tma_prefetch_desc(&tmBlo);
-    for (int s = 0; s < F_SA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], SPLIT_THREADS); }
+    for (int s = 0; s < F_SA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], F_SPLIT_THREADS); }
     for (int s = 0; s < F_SB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-    for (int s = 0; s < F_ST; ++s) { mbar_init(&ta_full[s], SPLIT_THREADS); mbar_init(&ta_empty[s], 1); }
+    for (int s = 0; s < F_ST; ++s) { mbar_init(&ta_full[s], F_SPLIT_THREADS); mbar_init(&ta_empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], EPI_THREADS); }
     mbar_init(small_empty, EPI_THREADS);
     mbar_fence_init();
@@ -559,40 +557,45 @@ conv_gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   if (warp < 8) {
     // ---------------- operand splitter: raw fp32 row in smem -> fp16 (hi, lo * 2^11) pairs in the TMEM A ring ----------------
     reg_dec<F_REGS_SPLIT>();
-    const int g = warp >> 2;                  // group: handles running k-blocks kbt == g (mod 2)
+    const int g = warp >> 2;                  // group = 32-channel half of the k-block
     const int q = warp & 3;                   // TMEM lane quarter
     const int row = q * 32 + lane;
     const uint32_t lane_field = (uint32_t)(q * 32) << 16;
     int total_kb = 0;                         // k-blocks of all units of this CTA (the splitter needs nothing else about them)
     for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) total_kb += decode_unit(p, u, num_kb_total).num_kb;
-    int sa = g; uint32_t pa = 0;
+    int sa = 0; uint32_t pa = 0;
 #pragma unroll 1
-    for (int kbt = g; kbt < total_kb; kbt += 2) {
+    for (int kbt = 0; kbt < total_kb; ++kbt) {
       MBAR_WAIT(&a_full[sa], pa, 1, kbt);
       // SWIZZLE_128B: 16-byte chunk c of row r sits at chunk (c ^ (r & 7)); quarter-warp phases are conflict-free
-      const uint8_t* arow = smem_a + sa * A_TILE_BYTES + row * 128;
+      const uint8_t* arow = smem_a + sa * F_A_STAGE + g * A_TILE_BYTES + row * 128;
       uint32_t pk[32];                        // [0,16): hi pairs (k, k+1), [16,32): lo pairs
+      if (p.dbg & 1) {
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const float4 v = *reinterpret_cast<const float4*>(arow + ((c ^ (row & 7)) << 4));
-        const uint32_t h01 = pack_f16x2_sat(v.x, v.y), h23 = pack_f16x2_sat(v.z, v.w);
-        const float2 f01 = __half22float2(*reinterpret_cast<const __half2*>(&h01));
-        const float2 f23 = __half22float2(*reinterpret_cast<const __half2*>(&h23));
-        pk[2 * c] = h01; pk[2 * c + 1] = h23;
-        pk[16 + 2 * c] = pack_f16x2_sat(__fmul_rn(__fsub_rn(v.x, f01.x), 2048.f), __fmul_rn(__fsub_rn(v.y, f01.y), 2048.f));
-        pk[16 + 2 * c + 1] = pack_f16x2_sat(__fmul_rn(__fsub_rn(v.z, f23.x), 2048.f), __fmul_rn(__fsub_rn(v.w, f23.y), 2048.f));
+        for (int j = 0; j < 32; ++j) pk[j] = 0u;
+      } else {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float4 v = *reinterpret_cast<const float4*>(arow + ((c ^ (row & 7)) << 4));
+          const uint32_t h01 = pack_f16x2_sat(v.x, v.y), h23 = pack_f16x2_sat(v.z, v.w);
+          const float2 f01 = __half22float2(*reinterpret_cast<const __half2*>(&h01));
+          const float2 f23 = __half22float2(*reinterpret_cast<const __half2*>(&h23));
+          pk[2 * c] = h01; pk[2 * c + 1] = h23;
+          pk[16 + 2 * c] = pack_f16x2_sat(__fmul_rn(__fsub_rn(v.x, f01.x), 2048.f), __fmul_rn(__fsub_rn(v.y, f01.y), 2048.f));
+          pk[16 + 2 * c + 1] = pack_f16x2_sat(__fmul_rn(__fsub_rn(v.z, f23.x), 2048.f), __fmul_rn(__fsub_rn(v.w, f23.y), 2048.f));
+        }
       }
       // raw tile consumed: the arrive carries a data dependency on every one of the 8 row loads, so it cannot be issued
-      // while a load is still outstanding (the A producer re-fills the slot as soon as all 128 threads arrived)
+      // while a load is still outstanding (the A producer re-fills the stage as soon as all 256 threads arrived)
       mbar_arrive_after(&a_empty[sa], (pk[0] | pk[2] | pk[4]) | (pk[6] | pk[8] | pk[10]) | (pk[12] | pk[14]));
       const int st = kbt & (F_ST - 1);
-      MBAR_WAIT(&ta_empty[st], (((uint32_t)kbt >> 2) & 1u) ^ 1u, 2, kbt);   // TMEM slot no longer read by the tensor core
+      MBAR_WAIT(&ta_empty[st], (((uint32_t)kbt >> 1) & 1u) ^ 1u, 2, kbt);   // TMEM slot no longer read by the tensor core
       tc_fence_after();
-      tmem_st_32x32(tmem_base + lane_field + (uint32_t)(F_TMEM_A0 + st * 32), pk);
+      tmem_st_32x32(tmem_base + lane_field + (uint32_t)(F_TMEM_A0 + st * 64 + g * 32), pk);
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&ta_full[st]);
-      sa += 2; if (sa >= F_SA) { sa -= F_SA; pa ^= 1u; }
+      if (++sa == F_SA) { sa = 0; pa ^= 1u; }
     }
   } else if (warp < 16) {
     // ---------------- accumulate (TMEM chunk partials -> fp32 registers, RN adds) + epilogue ----------------
@@ -614,6 +617,7 @@ conv_gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         const uint32_t b = ct & 1u;
         MBAR_WAIT(&acc_full[b], (ct >> 1) & 1u, 3, ct);
         tc_fence_after();
+        if (!(p.dbg & 16))
 #pragma unroll
         for (int c0 = 0; c0 < W; c0 += 32) {
           uint32_t v[32];
@@ -644,20 +648,28 @@ conv_gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     reg_dec<F_REGS_CTRL>();
     if (warp == 16 && lane == 0) {
       // ---------------- TMA producer, activations ----------------
-      const int cchunks = p.cin / BLOCK_K;
+      const int cchunks = p.cin / BLOCK_K;                        // 32-channel chunks per filter tap
+      const int total32 = p.kh * p.kw * cchunks;
       pdl_wait();                             // the input belongs to the previous kernel until it completed
       int sa = 0; uint32_t pa = 0;
       for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
         const Unit t = decode_unit(p, u, num_kb_total);
 #pragma unroll 1
         for (int kb = 0; kb < t.num_kb; ++kb) {
-          const int gk = t.kb0 + kb;                              // global k-block -> (filter tap, channel chunk)
-          const int tap = gk / cchunks, kc = gk - tap * cchunks;
-          const int r = tap / p.kw, s = tap - r * p.kw;
-          MBAR_WAIT(&a_empty[sa], pa ^ 1u, 4, kb);                       // a splitter group has consumed the raw tile
-          mbar_expect_tx(&a_full[sa], (uint32_t)p.a_box_bytes);
-          tma_load_4d(smem_a + sa * A_TILE_BYTES, &tmA, &a_full[sa], kc * BLOCK_K, t.w0 * p.stride + s - p.pad_l,
-                      t.h0 * p.stride + r - p.pad_t, t.n0);
+          MBAR_WAIT(&a_empty[sa], pa ^ 1u, 4, kb);                // both splitter groups have consumed the stage
+          if (p.dbg & 4) mbar_arrive(&a_full[sa]);
+          else {
+            mbar_expect_tx(&a_full[sa], (uint32_t)(2 * p.a_box_bytes));
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const int g32 = (t.kb0 + kb) * 2 + i;               // global 32-channel block -> (filter tap, channel chunk)
+              int tap = g32 / cchunks, kc = g32 - tap * cchunks;
+              if (g32 >= total32) { tap = 0; kc = cchunks; }      // odd tail: a box past the last channel is zero-filled by TMA
+              const int r = tap / p.kw, s = tap - r * p.kw;
+              tma_load_4d(smem_a + sa * F_A_STAGE + i * A_TILE_BYTES, &tmA, &a_full[sa], kc * BLOCK_K, t.w0 * p.stride + s - p.pad_l,
+                          t.h0 * p.stride + r - p.pad_t, t.n0);
+            }
+          }
           if (++sa == F_SA) { sa = 0; pa ^= 1u; }
         }
       }
@@ -668,51 +680,62 @@ conv_gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         const Unit t = decode_unit(p, u, num_kb_total);
 #pragma unroll 1
         for (int kb = 0; kb < t.num_kb; ++kb) {
-          const int kcoord = (t.kb0 + kb) * BLOCK_K;              // K axis of the packed weights = (tap, cin) flattened
-          MBAR_WAIT(&b_empty[sb], pb ^ 1u, 5, kb);                       // the MMAs that read this slot completed
-          mbar_expect_tx(&b_full[sb], (uint32_t)kBStage);
-          tma_load_2d(smem_b + sb * kBStage, &tmBhi, &b_full[sb], kcoord, t.nblk * BN);
-          tma_load_2d(smem_b + sb * kBStage + kBTile, &tmBlo, &b_full[sb], kcoord, t.nblk * BN);
+          const int kcoord = (t.kb0 + kb) * F_BK;                 // K axis of the packed weights = (tap, cin) flattened; past the end: zeros
+          MBAR_WAIT(&b_empty[sb], pb ^ 1u, 5, kb);                // the MMAs that read this slot completed
+          if (p.dbg & 8) mbar_arrive(&b_full[sb]);
+          else {
+            mbar_expect_tx(&b_full[sb], (uint32_t)kBStage);
+            tma_load_2d(smem_b + sb * kBStage, &tmBhi, &b_full[sb], kcoord, t.nblk * BN);
+            tma_load_2d(smem_b + sb * kBStage + kBTile, &tmBlo, &b_full[sb], kcoord, t.nblk * BN);
+          }
           if (++sb == F_SB) { sb = 0; pb ^= 1u; }
         }
       }
-    } else if (warp == 18 && lane == 0) {
-      // ---------------- MMA issuer ----------------
+    } else if (warp == 18) {
+      // ---------------- MMA issuer: the whole warp walks the loop converged (operands in uniform registers) ----------------
+      const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
       uint32_t kbt = 0, ct = 0, ut = 0;
       int sb = 0; uint32_t pb = 0;
-      const uint32_t d_small = tmem_base + (uint32_t)F_TMEM_DSMALL;
+      const uint32_t d_small = tb + (uint32_t)F_TMEM_DSMALL;
+      const uint32_t sb0 = smem_u32(smem_b);
+      const int kpc = p.kb_per_chunk;
       for (int u = blockIdx.x; u < p.total_units; u += gridDim.x, ++ut) {
         const Unit t = decode_unit(p, u, num_kb_total);
+        const int nkb = __shfl_sync(0xffffffffu, t.num_kb, 0);
         int in_chunk = 0;
 #pragma unroll 1
-        for (int kb = 0; kb < t.num_kb; ++kb, ++kbt) {
+        for (int kb = 0; kb < nkb; ++kb, ++kbt) {
           const uint32_t b = ct & 1u;
           if (in_chunk == 0) MBAR_WAIT(&acc_empty[b], ((ct >> 1) & 1u) ^ 1u, 6, kbt);   // D_main[b]'s previous chunk has been drained
           if (kb == 0) MBAR_WAIT(small_empty, (ut & 1u) ^ 1u, 7, kbt);                  // D_small of the previous unit has been read
           const uint32_t st = kbt & (uint32_t)(F_ST - 1);
-          MBAR_WAIT(&ta_full[st], (kbt >> 2) & 1u, 8, kbt);
+          MBAR_WAIT(&ta_full[st], (kbt >> 1) & 1u, 8, kbt);
           MBAR_WAIT(&b_full[sb], pb, 9, kbt);
           tc_fence_after();
-          const uint32_t sbase = smem_u32(smem_b + sb * kBStage);
-          const uint64_t b_hi = sw64_desc(sbase);
-          const uint64_t b_lo = sw64_desc(sbase + kBTile);
-          const uint32_t a_hi = tmem_base + (uint32_t)F_TMEM_A0 + st * 32u;
-          const uint32_t a_lo = a_hi + 16u;
-          const uint32_t d_main = tmem_base + b * 128u;
+          const uint32_t sbase = sb0 + (uint32_t)(sb * kBStage);
+          const uint64_t b_hi = sw128_desc(sbase);
+          const uint64_t b_lo = sw128_desc(sbase + kBTile);
+          const uint32_t a0 = tb + (uint32_t)F_TMEM_A0 + st * 64u;
+          const uint32_t d_main = tb + b * 128u;
+          const bool last = (in_chunk + 1 == kpc) || (kb + 1 == nkb);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / 16; ++k) {
-            const uint64_t off = (uint64_t)(k * 16 * 2) >> 4;  // B: advance 16 fp16 = 32 B inside the swizzle row
-            const uint32_t ak = (uint32_t)(k * 8);             // A: 16 fp16 = 8 TMEM columns
-            umma_f16_ts(d_small, a_lo + ak, b_hi + off, kIdesc, (k > 0 || kb > 0) ? 1u : 0u);
-            umma_f16_ts(d_small, a_hi + ak, b_lo + off, kIdesc, 1u);
-            umma_f16_ts(d_main, a_hi + ak, b_hi + off, kIdesc, (k > 0 || in_chunk > 0) ? 1u : 0u);
+            for (int j = 0; j < F_BK / 16; ++j) {
+              const uint64_t off = (uint64_t)(j * 16 * 2) >> 4;               // B: advance 16 fp16 = 32 B inside the 128-byte swizzle row
+              const uint32_t a_hi = a0 + (uint32_t)((j >> 1) * 32 + (j & 1) * 8);   // A: 32-channel half, then 16 fp16 = 8 TMEM columns
+              const uint32_t a_lo = a_hi + 16u;
+              if (!(p.dbg & 2)) {
+                umma_f16_ts(d_small, a_lo, b_hi + off, kIdesc, (j > 0 || kb > 0) ? 1u : 0u);
+                umma_f16_ts(d_small, a_hi, b_lo + off, kIdesc, 1u);
+              }
+              umma_f16_ts(d_main, a_hi, b_hi + off, kIdesc, (j > 0 || in_chunk > 0) ? 1u : 0u);
+            }
+            umma_commit(&ta_empty[st]);
+            umma_commit(&b_empty[sb]);
+            if (last) umma_commit(&acc_full[b]);
           }
-          umma_commit(&ta_empty[st]);
-          umma_commit(&b_empty[sb]);
-          if (++in_chunk == p.kb_per_chunk || kb + 1 == t.num_kb) {
-            umma_commit(&acc_full[b]);
-            in_chunk = 0; ++ct;
-          }
+          __syncwarp();
+          if (last) { in_chunk = 0; ++ct; } else ++in_chunk;
           if (++sb == F_SB) { sb = 0; pb ^= 1u; }
         }
       }
@@ -939,9 +962,10 @@ static int decide_geometry(const frcnn_conv_desc* d, int sms, Geometry* g) {
   choose_tile(g->n, g->ho, g->wo, d->stride, &g->tn, &g->th, &g->tw);
   g->tiles_w = cdiv(g->wo, g->tw); g->tiles_h = cdiv(g->ho, g->th); g->tiles_n = cdiv(g->n, g->tn);
   g->m_tiles = (long)g->tiles_w * g->tiles_h * g->tiles_n;
-  g->num_kb = d->kh * d->kw * d->cin / BLOCK_K;
   const bool f16 = d->impl != FRCNN_CONV_TF32X3;
-  g->kpc = d->kb_per_chunk > 0 ? d->kb_per_chunk : 8;
+  const int ks = f16 ? 2 : 1;                                   // 32-channel blocks per k-block (f16x3: 64-wide k-blocks)
+  g->num_kb = cdiv(d->kh * d->kw * d->cin / BLOCK_K, ks);
+  g->kpc = d->kb_per_chunk > 0 ? d->kb_per_chunk : 8 / ks;
   int bn = d->block_n;
   if (bn == 0) {
     long best = -1;
@@ -953,7 +977,7 @@ static int decide_geometry(const frcnn_conv_desc* d, int sms, Geometry* g) {
       const long waves = (ctas + sms - 1) / sms;
       // measured (profiles/r01): a k-block costs about the same whatever block_n is (the 128-row A operand dominates for
       // N <= 128), plus a fixed per-unit cost => fewest rounds wins, widest tile on ties
-      const long cost = f16 ? waves * (g->num_kb * 500L + 4000L) : waves * (g->num_kb * 1400L + 6000L);
+      const long cost = f16 ? waves * (g->num_kb * 900L + 4000L) : waves * (g->num_kb * 1400L + 6000L);
       if (best < 0 || cost < best) { best = cost; bn = c; }
     }
   }
@@ -965,15 +989,15 @@ static int decide_geometry(const frcnn_conv_desc* d, int sms, Geometry* g) {
   // ---- whole tiles + K-split tail (see ConvKernelParams) ---------------------------------------------------------------
   long n_tail = 0; int splits = 1;
   const int num_kb = g->num_kb;
-  const int max_split = num_kb / 8 < 8 ? num_kb / 8 : 8;        // >= 8 k-blocks (one chunk) per split, at most 8 splits
+  const int max_split = num_kb * ks / 8 < 8 ? num_kb * ks / 8 : 8;   // >= 8 32-wide k-blocks (one chunk) per split, at most 8 splits
   if (d->split_k > 1) {                                         // forced: every tile is split
     n_tail = g->tiles; splits = d->split_k;
   } else if (d->split_k == 0 && max_split >= 2) {
     const long rem = g->tiles % sms;
     // measured (r01): a split unit still pays ~7 us of per-unit overhead and the reduce pass ~10 us, so the ragged round is
     // only worth splitting when the K loop is long (>= 48 k-blocks); small layers gain from 16 k-blocks on.
-    if (g->tiles <= sms / 2) { if (num_kb >= 16) { n_tail = g->tiles; splits = (int)(sms / g->tiles); } }   // layer too small to fill the GPU
-    else if (g->tiles > sms && rem > 0 && rem <= sms / 2 && num_kb >= 48) { n_tail = rem; splits = (int)(sms / rem); }   // ragged last round
+    if (g->tiles <= sms / 2) { if (num_kb * ks >= 16) { n_tail = g->tiles; splits = (int)(sms / g->tiles); } }   // layer too small to fill the GPU
+    else if (g->tiles > sms && rem > 0 && rem <= sms / 2 && num_kb * ks >= 48) { n_tail = rem; splits = (int)(sms / rem); }   // ragged last round
     if (splits > max_split) splits = max_split;
     if (splits < 2) { n_tail = 0; splits = 1; }
   }
@@ -1025,10 +1049,10 @@ extern "C" int frcnn_conv_plan_create(frcnn_conv_plan** out, const frcnn_conv_de
     const uint64_t ktot = (uint64_t)d->kh * d->kw * d->cin;
     uint64_t dims[2] = {ktot, (uint64_t)d->cout};
     uint64_t strides[1] = {ktot * (f16 ? 2 : 4)};
-    uint32_t box[2] = {(uint32_t)BLOCK_K, (uint32_t)bn};
+    uint32_t box[2] = {(uint32_t)(f16 ? F_BK : BLOCK_K), (uint32_t)bn};   // 128-byte rows either way
     uint32_t es[2] = {1, 1};
     const CUtensorMapDataType dt = f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
-    const CUtensorMapSwizzle sw = f16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+    const CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_128B;
     int rc = encode_map(&p->tmBhi, d->w_hi_dev, 2, dims, strides, box, es, dt, sw);
     if (!rc) rc = encode_map(&p->tmBlo, d->w_lo_dev, 2, dims, strides, box, es, dt, sw);
     if (rc) { free(p); return rc; }
@@ -1042,6 +1066,8 @@ extern "C" int frcnn_conv_plan_create(frcnn_conv_plan** out, const frcnn_conv_de
   k.a_box_bytes = g.tn * g.th * g.tw * BLOCK_K * 4;
   k.kb_per_chunk = g.kpc;
   k.trace = nullptr;
+  { const char* e = getenv("FRCNN_CONV_DBG"); k.dbg = e ? atoi(e) : 0; }
+  k.num_kb_total = g.num_kb;
   k.out_mult = f16 ? (d->out_mult != 0.f ? d->out_mult : 1.f) : 1.f;
   k.m_tiles = (int)g.m_tiles; k.n_tiles = g.n_tiles;
   k.kb_per_split = g.kbs; k.splits = g.splits; k.n_full = (int)(g.tiles - g.n_tail);

@@ -89,14 +89,30 @@ def one(name, n, h, w, cin, cout, k, impl, kpc=0, bn=0, check=True, reps=20, str
     return True
 
 
+def ablate():
+    shapes = [("res_head_c3", 300, 7, 7, 512, 512, 3), ("res_head_pw512_2048", 300, 7, 7, 512, 2048, 1), ("res_b3_pw1024_256", 1, 38, 50, 1024, 256, 1),
+              ("res_b3_c3_256", 1, 38, 50, 256, 256, 3), ("res_b3_pw256_1024", 1, 38, 50, 256, 1024, 1)]
+    for s in shapes:
+        for dbg in (0, 1, 2, 4, 8, 16, 3, 12, 15, 31):
+            os.environ["FRCNN_CONV_DBG"] = str(dbg)
+            print("dbg=%-2d" % dbg, end=" ")
+            one(*s, impl=0, kpc=4, check=False)
+    os.environ["FRCNN_CONV_DBG"] = "0"
+
+
 def main():
     mode = sys.argv[1] if len(sys.argv) > 1 else "quick"
+    if mode == "ablate":
+        return ablate()
+    if mode == "ncu":
+        one("res_head_c3", 300, 7, 7, 512, 512, 3, impl=0, kpc=4, check=False, reps=2)
+        return one("res_b3_c3_256", 1, 38, 50, 256, 256, 3, impl=0, kpc=4, check=False, reps=2)
     print("lib:", N.LIB_PATH, "watchdog:", watchdog() is not None, flush=True)
     t0 = time.time()
     # ---- correctness first, smallest first ----------------------------------------------------------------------------
     small = [("fc_small", 1, 1, 300, 64, 64, 1), ("pw_1900", 1, 38, 50, 256, 256, 1), ("c3_64", 1, 38, 50, 64, 64, 3),
              ("c3_odd_cout", 1, 20, 30, 128, 96, 3), ("rois_c3", 20, 7, 7, 64, 64, 3), ("rpn_cout72", 1, 38, 50, 512, 72, 1),
-             ("fc_k3136", 1, 1, 300, 3136, 128, 1), ("pw_cin32", 1, 38, 50, 32, 64, 1)]
+             ("fc_k3136", 1, 1, 300, 3136, 128, 1), ("pw_cin32", 1, 38, 50, 32, 64, 1), ("c3_cin96", 1, 20, 30, 96, 64, 3)]
     ok = True
     for s in small:
         ok = one(*s, impl=0) and ok
@@ -114,7 +130,7 @@ def main():
            ("res_b1_pw64_256", 1, 150, 200, 64, 256, 1), ("res_b2_c3_128", 1, 75, 100, 128, 128, 3)]
     for s in big:
         chk = mode == "full" or s[0] in ("res_head_c3", "res_b3_pw1024_256")
-        for kpc in ((4, 8, 16) if s[0] in ("res_head_c3", "res_head_pw2048_512") else (8,)):
+        for kpc in ((2, 4, 8) if s[0] in ("res_head_c3", "res_head_pw2048_512") else (4,)):
             one(*s, impl=0, kpc=kpc, check=chk)
         one(*s, impl=1, kpc=8, check=False)
         if time.time() - t0 > 420:
