@@ -68,7 +68,8 @@ def test_same_padding_tiny_known_answer():
     w = np.ones((1, 3, 1, 1), F)
     assert L.conv2d(x, w, 2, "SAME").ravel().tolist() == [111.0, 1100.0]
     # slim conv2d_same (explicit pad (k-1)//2 = 1 on both sides, then VALID): out = [0+x0+x1, x1+x2+x3]
-    assert L.conv2d_same(x.reshape(1, 4, 1, 1), np.ones((3, 1, 1, 1), F), 2)[0, :, 0, 0].tolist() == [11.0, 1110.0]
+    wc = np.zeros((3, 3, 1, 1), F); wc[:, 1] = 1              # only the centre column is non-zero: a 1-D filter along H
+    assert L.conv2d_same(x.reshape(1, 4, 1, 1), wc, 2)[0, :, 0, 0].tolist() == [11.0, 1110.0]
 
 
 @pytest.mark.parametrize("stride,mode", [(2, "SAME"), (2, "EXPLICIT"), (1, "SAME")])
