@@ -60,8 +60,8 @@ constexpr int TMEM_A_COL0 = 256;
 struct ConvKernelParams {
   float* out;
   const float* residual;
-  const float* scale;
-  const float* shift;
+  const float* scale;   // [n_tiles*BN] plan-owned: (scale or 1) * out_mult (out_mult = 2^-wexp undoes the f16x3 weight scaling, exact)
+  const float* shift;   // [n_tiles*BN] plan-owned: shift or 0
   int cout, ho, wo, nimg;
   int tn, th, tw;
   int tiles_h, tiles_w;
@@ -72,7 +72,8 @@ struct ConvKernelParams {
   // Work units.  Tiles t = mt + m_tiles*nblk.  Units [0, n_full) are whole tiles (direct epilogue).  The remaining
   // `n_tail` tiles -- the ragged last round of the persistent loop, or every tile of a layer too small to fill the GPU --
   // are each split over `splits` units along K: unit n_full + v -> tile n_full + v / splits, split v % splits, which writes
-  // its raw partial tile to ws[(v / splits)][v % splits][128][BN]; tail_reduce_kernel sums them in index order.
+  // its raw partial tile to ws[(v / splits)][v % splits][128][BN]; tail_reduce_kernel sums them in index order and
+  // runs the epilogue (r02 measured an in-kernel 'last CTA to arrive reduces' fix-up: 21 us instead of 13 us for a 38x50 1x1 layer).
   int kb_per_split;
   int m_tiles, n_tiles, total_units, n_full, splits;
   float* ws;
@@ -80,7 +81,6 @@ struct ConvKernelParams {
   int num_kb_total;   // f16x3: 64-wide k-blocks of the whole K loop
   int dbg;            // development ablations (FRCNN_CONV_DBG, read at plan creation): 1 splitter skips load+convert, 2 MMA issues only
                       // the hi*hi product, 4 / 8 producer A / B skip their TMA, 16 epilogue skips the chunk promotion loads.  0 in production.
-  float out_mult;     // f16x3: 2^-wexp, undoes the power-of-two weight scaling (exact); tf32x3: 1
 };
 
 #define FRCNN_TRACE2(base, idx)                                                             \
@@ -132,20 +132,132 @@ __device__ __forceinline__ Unit decode_unit(const ConvKernelParams& p, int u, in
 // ---------------- tile epilogue shared by both kernels (overlaps the next unit's main loop) ----------------
 // `acc` = this thread's W = BN/2 fp32 sums of output row (q*32 + lane), columns [col0, col0 + W) of the tile; ew = index of the
 // epilogue warp (0..7) = its 4 KB slice of the transposition buffer.
+//
+// r01 finding 4: writing each thread's own output row straight from registers (32 lanes = 32 rows, 8 KB apart) made every
+// global access 32 separate sectors.  The tile is transposed through shared memory 32 columns at a time: thread = row writes
+// XOR-swizzled 16-byte chunks (conflict free), then each lane owns 4 fixed channels and walks the warp's rows with coalesced
+// 128-bit accesses (one full 128-byte line per row).  r01 finding 5: epilogue inputs are loaded with pinned (asm volatile)
+// loads -- with __ldg the compiler sank the loads into the row loop.
+// r02 finding 3 (ncu source page, head 1x1 512->2048): the generic epilogue -- every flag a run-time test per element, scalar
+// tails, `continue`s that stop the scheduler from overlapping rows -- executed ~2500 instructions per warp per tile and took
+// ~20 000 cycles, 3x the tile's MMA time: short-K layers were EPILOGUE bound.  Hence: p.scale / p.shift are always present
+// (plan-owned vectors padded to the tile grid, scale pre-multiplied by the exact power-of-two out_mult), residual and
+// activation are template parameters, and rows are computed unconditionally with only the store predicated.
+constexpr int EPI_CH = 8;                                  // 16-byte chunks per staged 32-column row
+constexpr int EPI_ROWS_PER_IT = 4;
+constexpr int EPI_ITERS = 8;
+
+template <int ACT>
+__device__ __forceinline__ float apply_act(float a) {
+  if (ACT == FRCNN_ACT_RELU) return fmaxf(a, 0.f);
+  if (ACT == FRCNN_ACT_RELU6) return fminf(fmaxf(a, 0.f), 6.f);
+  return a;
+}
+
+// y = act(v*scale + shift (+ res)) with one rounding per operation (the oracle's order: tf.nn.batch_normalization /
+// bias_add, then the shortcut add, then the activation)
+template <bool RES, int ACT>
+__device__ __forceinline__ float4 finish4(const float4 v, const float4 sc, const float4 sh, const float4 r) {
+  float4 y;
+  y.x = __fadd_rn(__fmul_rn(v.x, sc.x), sh.x); y.y = __fadd_rn(__fmul_rn(v.y, sc.y), sh.y);
+  y.z = __fadd_rn(__fmul_rn(v.z, sc.z), sh.z); y.w = __fadd_rn(__fmul_rn(v.w, sc.w), sh.w);
+  if (RES) { y.x = __fadd_rn(y.x, r.x); y.y = __fadd_rn(y.y, r.y); y.z = __fadd_rn(y.z, r.z); y.w = __fadd_rn(y.w, r.w); }
+  y.x = apply_act<ACT>(y.x); y.y = apply_act<ACT>(y.y); y.z = apply_act<ACT>(y.z); y.w = apply_act<ACT>(y.w);
+  return y;
+}
+
+// whole tile, cout % 4 == 0: stage -> coalesced float4 stores
+template <int BN, bool RES, int ACT>
+__device__ __forceinline__ void epilogue_vec(const ConvKernelParams& p, const int cbase, const float (&acc)[BN / 2], float4* stage,
+                                             const int lane, const int my_pix) {
+  constexpr int W = BN / 2;
+  const int cg = lane & (EPI_CH - 1), rsub = lane >> 3;
+  const int cout = p.cout;
+  int pixr[EPI_ITERS];
+#pragma unroll
+  for (int it = 0; it < EPI_ITERS; ++it) pixr[it] = __shfl_sync(0xffffffffu, my_pix, it * EPI_ROWS_PER_IT + rsub);
+#pragma unroll
+  for (int pass = 0; pass < W / 32; ++pass) {
+    const int c = cbase + pass * 32 + cg * 4;              // first of this lane's 4 output channels in this pass
+    const bool col_ok = c < cout;
+    const float4 sc = ld_nc_f4_pinned(p.scale + c);        // padded to the tile grid: always in bounds
+    const float4 sh = ld_nc_f4_pinned(p.shift + c);
+    __syncwarp();                                           // previous pass's reads are done
+#pragma unroll
+    for (int j = 0; j < EPI_CH; ++j) {
+      const int a0 = pass * 32 + 4 * j;
+      stage[lane * EPI_CH + ((j ^ lane) & (EPI_CH - 1))] = make_float4(acc[a0], acc[a0 + 1], acc[a0 + 2], acc[a0 + 3]);
+    }
+    // residual rows of this pass: issued after the pass's accumulators are staged (their registers are free again)
+    float4 rv[EPI_ITERS];
+    if (RES) {
+#pragma unroll
+      for (int it = 0; it < EPI_ITERS; ++it)
+        rv[it] = (pixr[it] >= 0 && col_ok) ? ld_nc_f4_pinned(p.residual + (size_t)pixr[it] * cout + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < EPI_ITERS; ++it) {
+      const int r = it * EPI_ROWS_PER_IT + rsub;
+      const float4 v = stage[r * EPI_CH + ((cg ^ r) & (EPI_CH - 1))];
+      const float4 y = finish4<RES, ACT>(v, sc, sh, RES ? rv[it] : v);
+      if (pixr[it] >= 0 && col_ok) *reinterpret_cast<float4*>(p.out + (size_t)pixr[it] * cout + c) = y;
+    }
+  }
+}
+
+// any cout (scalar tails): same arithmetic, run-time flags
+template <int BN>
+__device__ __forceinline__ void epilogue_generic(const ConvKernelParams& p, const int cbase, const float (&acc)[BN / 2], float4* stage,
+                                                 const int lane, const int my_pix) {
+  constexpr int W = BN / 2;
+  const int cg = lane & (EPI_CH - 1), rsub = lane >> 3;
+#pragma unroll
+  for (int pass = 0; pass < W / 32; ++pass) {
+    const int c = cbase + pass * 32 + cg * 4;
+    const float4 sc4 = ld_nc_f4_pinned(p.scale + c), sh4 = ld_nc_f4_pinned(p.shift + c);
+    const float sc[4] = {sc4.x, sc4.y, sc4.z, sc4.w}, sh[4] = {sh4.x, sh4.y, sh4.z, sh4.w};
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < EPI_CH; ++j) {
+      const int a0 = pass * 32 + 4 * j;
+      stage[lane * EPI_CH + ((j ^ lane) & (EPI_CH - 1))] = make_float4(acc[a0], acc[a0 + 1], acc[a0 + 2], acc[a0 + 3]);
+    }
+    __syncwarp();
+#pragma unroll 1
+    for (int it = 0; it < EPI_ITERS; ++it) {
+      const int r = it * EPI_ROWS_PER_IT + rsub;
+      const int pix = __shfl_sync(0xffffffffu, my_pix, r);
+      if (pix < 0) continue;
+      const float4 v = stage[r * EPI_CH + ((cg ^ r) & (EPI_CH - 1))];
+      const float y[4] = {v.x, v.y, v.z, v.w};
+      float* optr = p.out + (size_t)pix * p.cout + c;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (c + e >= p.cout) break;
+        float a = __fadd_rn(__fmul_rn(y[e], sc[e]), sh[e]);
+        if (p.residual) a = __fadd_rn(a, __ldg(p.residual + (size_t)pix * p.cout + c + e));
+        if (p.act == FRCNN_ACT_RELU) a = fmaxf(a, 0.f);
+        else if (p.act == FRCNN_ACT_RELU6) a = fminf(fmaxf(a, 0.f), 6.f);
+        optr[e] = a;
+      }
+    }
+  }
+}
+
+template <int BN, bool RES>
+__device__ __forceinline__ void epilogue_dispatch(const ConvKernelParams& p, const int cbase, const float (&acc)[BN / 2], float4* stage,
+                                                  const int lane, const int my_pix) {
+  if (p.act == FRCNN_ACT_RELU) epilogue_vec<BN, RES, FRCNN_ACT_RELU>(p, cbase, acc, stage, lane, my_pix);
+  else if (p.act == FRCNN_ACT_RELU6) epilogue_vec<BN, RES, FRCNN_ACT_RELU6>(p, cbase, acc, stage, lane, my_pix);
+  else epilogue_vec<BN, RES, FRCNN_ACT_NONE>(p, cbase, acc, stage, lane, my_pix);
+}
+
 template <int BN>
 __device__ __forceinline__ void epilogue_tile(const ConvKernelParams& p, const Unit& t, const float (&acc)[BN / 2],
                                               uint8_t* smem_stage, int ew, int q, int lane) {
   constexpr int W = BN / 2;
   const int col0 = (ew >> 2) * W;
-  const float om = p.out_mult;
-  // r01 finding 4: writing each thread's own output row straight from registers (32 lanes = 32 rows, 8 KB apart) made
-  // every global access 32 separate sectors.  The tile is transposed through shared memory 32 columns at a time: thread =
-  // row writes XOR-swizzled 16-byte chunks (conflict free), then each lane owns 4 fixed channels and walks the warp's rows
-  // with coalesced 128-bit accesses (one full 128-byte line per row).  r01 finding 5: epilogue inputs are loaded with
-  // pinned (asm volatile) loads -- with __ldg the compiler sank the scale/shift loads into the row loop.
-  constexpr int CH = 8;                                   // 16-byte chunks per staged 32-column row
-  constexpr int ROWS_PER_IT = 4;
-  constexpr int ITERS = 8;
   float4* stage = reinterpret_cast<float4*>(smem_stage + ew * (32 * 32 * 4));
   const int row = q * 32 + lane;
   const int rows_img = p.th * p.tw;
@@ -153,92 +265,37 @@ __device__ __forceinline__ void epilogue_tile(const ConvKernelParams& p, const U
   const int dh = rem / p.tw, dw = rem % p.tw;
   const int n = t.n0 + dn, h = t.h0 + dh, w = t.w0 + dw;
   const bool valid = (row < p.tn * rows_img) && n < p.nimg && h < p.ho && w < p.wo;
-  const int cg = lane & (CH - 1);                         // column group of this lane
+  const int cg = lane & (EPI_CH - 1);
   const int rsub = lane >> 3;
+  const int my_pix = valid ? (int)(((long long)n * p.ho + h) * p.wo + w) : -1;
+  const int cbase = t.nblk * BN + col0;
   if (t.slot >= 0) {
-    // split tile: plain partial sums in the tile-local [128][BN] workspace layout; the epilogue runs in tail_reduce_kernel
+    // split tile: raw partial sums into the tile-local [128][BN] workspace (row-major, coalesced through the transposition buffer)
     float* const wbase = p.ws + ((size_t)t.slot * p.splits + t.z) * (size_t)(BLOCK_M * BN) + (size_t)(q * 32) * BN + col0;
 #pragma unroll
     for (int pass = 0; pass < W / 32; ++pass) {
       __syncwarp();
 #pragma unroll
-      for (int j = 0; j < CH; ++j) {
+      for (int j = 0; j < EPI_CH; ++j) {
         const int a0 = pass * 32 + 4 * j;
-        stage[lane * CH + ((j ^ lane) & (CH - 1))] =
-            make_float4(__fmul_rn(acc[a0], om), __fmul_rn(acc[a0 + 1], om), __fmul_rn(acc[a0 + 2], om), __fmul_rn(acc[a0 + 3], om));
+        stage[lane * EPI_CH + ((j ^ lane) & (EPI_CH - 1))] = make_float4(acc[a0], acc[a0 + 1], acc[a0 + 2], acc[a0 + 3]);
       }
       __syncwarp();
 #pragma unroll
-      for (int it = 0; it < ITERS; ++it) {
-        const int r = it * ROWS_PER_IT + rsub;
-        *reinterpret_cast<float4*>(wbase + (size_t)r * BN + pass * 32 + cg * 4) = stage[r * CH + ((cg ^ r) & (CH - 1))];
+      for (int it = 0; it < EPI_ITERS; ++it) {
+        const int r = it * EPI_ROWS_PER_IT + rsub;
+        __stcg(reinterpret_cast<float4*>(wbase + (size_t)r * BN + pass * 32 + cg * 4), stage[r * EPI_CH + ((cg ^ r) & (EPI_CH - 1))]);
       }
     }
+    return;                                                // the epilogue of split tiles runs in tail_reduce_kernel
+  }
+  if ((p.cout & 3) != 0) {
+    // scalar-tail layers are never split (decide_geometry) -- generic path
+    epilogue_generic<BN>(p, cbase, acc, stage, lane, my_pix);
     return;
   }
-  const int my_pix = valid ? (int)(((long long)n * p.ho + h) * p.wo + w) : -1;
-  const bool vec_ok = (p.cout & 3) == 0;
-  float* const obase = p.out;
-  const float* const rbase = p.residual;
-  const float* const scale = p.scale;
-  const float* const shift = p.shift;
-  const int act = p.act;
-  int pixr[ITERS];
-#pragma unroll
-  for (int it = 0; it < ITERS; ++it) pixr[it] = __shfl_sync(0xffffffffu, my_pix, it * ROWS_PER_IT + rsub);
-#pragma unroll
-  for (int pass = 0; pass < W / 32; ++pass) {
-    const int c = t.nblk * BN + col0 + pass * 32 + cg * 4;   // first of this lane's 4 output channels in this pass
-    const bool col_ok = c < p.cout;
-    float sc[4] = {1.f, 1.f, 1.f, 1.f}, sh[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int e = 0; e < 4; ++e)
-      if (c + e < p.cout) {
-        if (scale) sc[e] = ld_nc_f32_pinned(scale + c + e);
-        if (shift) sh[e] = ld_nc_f32_pinned(shift + c + e);
-      }
-    float4 rv[ITERS];
-    const bool res_vec = rbase && vec_ok;
-    if (res_vec) {
-#pragma unroll
-      for (int it = 0; it < ITERS; ++it)
-        rv[it] = (pixr[it] >= 0 && col_ok) ? ld_nc_f4_pinned(rbase + (size_t)pixr[it] * p.cout + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    __syncwarp();                                           // previous pass's reads are done
-#pragma unroll
-    for (int j = 0; j < CH; ++j) {
-      const int a0 = pass * 32 + 4 * j;
-      stage[lane * CH + ((j ^ lane) & (CH - 1))] = make_float4(acc[a0], acc[a0 + 1], acc[a0 + 2], acc[a0 + 3]);
-    }
-    __syncwarp();
-#pragma unroll
-    for (int it = 0; it < ITERS; ++it) {
-      if (pixr[it] < 0 || !col_ok) continue;
-      const int r = it * ROWS_PER_IT + rsub;
-      const float4 v = stage[r * CH + ((cg ^ r) & (CH - 1))];
-      float y[4] = {v.x, v.y, v.z, v.w};
-      float res[4] = {0.f, 0.f, 0.f, 0.f};
-      if (res_vec) { res[0] = rv[it].x; res[1] = rv[it].y; res[2] = rv[it].z; res[3] = rv[it].w; }
-      float* optr = obase + (size_t)pixr[it] * p.cout + c;
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        float a = __fmul_rn(y[e], om);   // exact: power of two
-        if (scale) a = __fmul_rn(a, sc[e]);
-        if (shift) a = __fadd_rn(a, sh[e]);
-        if (res_vec) a = __fadd_rn(a, res[e]);
-        else if (rbase && c + e < p.cout) a = __fadd_rn(a, __ldg(rbase + (size_t)pixr[it] * p.cout + c + e));
-        if (act == FRCNN_ACT_RELU) a = fmaxf(a, 0.f);
-        else if (act == FRCNN_ACT_RELU6) a = fminf(fmaxf(a, 0.f), 6.f);
-        y[e] = a;
-      }
-      if (vec_ok) {
-        *reinterpret_cast<float4*>(optr) = make_float4(y[0], y[1], y[2], y[3]);
-      } else {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) if (c + e < p.cout) optr[e] = y[e];
-      }
-    }
-  }
+  if (p.residual) epilogue_dispatch<BN, true>(p, cbase, acc, stage, lane, my_pix);
+  else epilogue_dispatch<BN, false>(p, cbase, acc, stage, lane, my_pix);
 }
 
 template <int BN>
@@ -617,17 +674,9 @@ conv_gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         const uint32_t b = ct & 1u;
         MBAR_WAIT(&acc_full[b], (ct >> 1) & 1u, 3, ct);
         tc_fence_after();
-        if (!(p.dbg & 16))
-#pragma unroll
-        for (int c0 = 0; c0 < W; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld_32x32(tq + b * 128u + (uint32_t)c0, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) acc[c0 + j] = __fadd_rn(acc[c0 + j], __uint_as_float(v[j]));
-        }
         if (c + 1 == num_chunks) {
-          // the cross terms of the unit's whole k range (complete: this acc_full commit covered every MMA), scaled by 2^11
+          // the cross terms of the unit's whole k range (complete: this acc_full commit covered every MMA), scaled by 2^11.
+          // Drained BEFORE the last chunk partial: D_small is single buffered, the next unit's first MMA waits for it.
 #pragma unroll
           for (int c0 = 0; c0 < W; c0 += 32) {
             uint32_t v[32];
@@ -638,6 +687,15 @@ conv_gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           }
           tc_fence_before();
           mbar_arrive(small_empty);           // the next unit's first MMA may overwrite D_small
+        }
+        if (!(p.dbg & 16))
+#pragma unroll
+        for (int c0 = 0; c0 < W; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(tq + b * 128u + (uint32_t)c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[c0 + j] = __fadd_rn(acc[c0 + j], __uint_as_float(v[j]));
         }
         tc_fence_before();
         mbar_arrive(&acc_empty[b]);           // the MMA warp may overwrite D_main[b]
@@ -768,13 +826,8 @@ tail_reduce_kernel(const ConvKernelParams p) {
   const int cg = threadIdx.x % C4;
   const int c = nblk * BN + cg * 4;
   if (c >= p.cout) return;
-  float sc[4] = {1.f, 1.f, 1.f, 1.f}, sh[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-  for (int e = 0; e < 4; ++e)
-    if (c + e < p.cout) {
-      if (p.scale) sc[e] = __ldg(p.scale + c + e);
-      if (p.shift) sh[e] = __ldg(p.shift + c + e);
-    }
+  const float4 sc4 = __ldg(reinterpret_cast<const float4*>(p.scale + c)), sh4 = __ldg(reinterpret_cast<const float4*>(p.shift + c));   // padded vectors
+  const float sc[4] = {sc4.x, sc4.y, sc4.z, sc4.w}, sh[4] = {sh4.x, sh4.y, sh4.z, sh4.w};
   {
     const int row = rgroup * RPB + threadIdx.x / C4;
     const int dn = row / rows_img, rem = row % rows_img;
@@ -796,8 +849,7 @@ tail_reduce_kernel(const ConvKernelParams p) {
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       float v = y[e];
-      if (p.scale) v = __fmul_rn(v, sc[e]);
-      if (p.shift) v = __fadd_rn(v, sh[e]);
+      v = __fadd_rn(__fmul_rn(v, sc[e]), sh[e]);
       if (p.residual) v = __fadd_rn(v, res[e]);
       if (p.act == FRCNN_ACT_RELU) v = fmaxf(v, 0.f);
       else if (p.act == FRCNN_ACT_RELU6) v = fminf(fmaxf(v, 0.f), 6.f);
@@ -806,6 +858,16 @@ tail_reduce_kernel(const ConvKernelParams p) {
     if (vec_ok) *reinterpret_cast<float4*>(p.out + o) = make_float4(y[0], y[1], y[2], y[3]);
     else for (int e = 0; e < 4; ++e) if (c + e < p.cout) p.out[o + e] = y[e];
   }
+}
+
+// plan creation: the epilogue's per-channel vectors, padded to the tile grid (no bounds tests in the kernel)
+__global__ void prep_epilogue_vectors_kernel(const float* scale, const float* shift, float out_mult, int cout, int padded,
+                                             float* eff_scale, float* eff_shift) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= padded) return;
+  const float sc = (c < cout && scale) ? scale[c] : 1.f;
+  eff_scale[c] = __fmul_rn(sc, out_mult);                  // exact: out_mult is a power of two
+  eff_shift[c] = (c < cout && shift) ? shift[c] : 0.f;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -857,7 +919,8 @@ struct frcnn_conv_plan {
   int impl;                // FRCNN_CONV_F16X3 | FRCNN_CONV_TF32X3
   dim3 grid;
   int n_tail;
-  float* ws;               // owned workspace of the split tiles
+  float* ws;               // owned workspace of the split tiles 
+  float* eff;              // owned epilogue vectors: scale * out_mult | shift, each padded to n_tiles * block_n
 };
 
 // choose the tile of output pixels (tn x th x tw <= 128) that needs the fewest tiles
@@ -1003,7 +1066,7 @@ static int decide_geometry(const frcnn_conv_desc* d, int sms, Geometry* g) {
   }
   int kbs = cdiv(num_kb, splits);                              // (a unit's last chunk may be shorter than kb_per_chunk)
   splits = cdiv(num_kb, kbs);
-  if (splits < 2) { n_tail = 0; splits = 1; }
+  if (splits < 2 || (d->cout & 3) != 0) { n_tail = 0; splits = 1; kbs = num_kb; }   // tail_reduce_kernel reads the padded epilogue vectors as float4
   FRCNN_REQUIRE(splits <= 64, "bad split_k");
   g->n_tail = n_tail; g->splits = splits; g->kbs = kbs;
   g->total_units = (g->tiles - n_tail) + n_tail * splits;
@@ -1058,7 +1121,7 @@ extern "C" int frcnn_conv_plan_create(frcnn_conv_plan** out, const frcnn_conv_de
     if (rc) { free(p); return rc; }
   }
   ConvKernelParams& k = p->kp;
-  k.out = d->out_dev; k.residual = d->residual_dev; k.scale = d->scale_dev; k.shift = d->shift_dev;
+  k.out = d->out_dev; k.residual = d->residual_dev;
   k.cout = d->cout; k.ho = g.ho; k.wo = g.wo; k.nimg = g.n;
   k.tn = g.tn; k.th = g.th; k.tw = g.tw; k.tiles_h = g.tiles_h; k.tiles_w = g.tiles_w;
   k.kh = d->kh; k.kw = d->kw; k.cin = d->cin; k.stride = d->stride; k.pad_t = d->pad_t; k.pad_l = d->pad_l;
@@ -1068,14 +1131,25 @@ extern "C" int frcnn_conv_plan_create(frcnn_conv_plan** out, const frcnn_conv_de
   k.trace = nullptr;
   { const char* e = getenv("FRCNN_CONV_DBG"); k.dbg = e ? atoi(e) : 0; }
   k.num_kb_total = g.num_kb;
-  k.out_mult = f16 ? (d->out_mult != 0.f ? d->out_mult : 1.f) : 1.f;
   k.m_tiles = (int)g.m_tiles; k.n_tiles = g.n_tiles;
   k.kb_per_split = g.kbs; k.splits = g.splits; k.n_full = (int)(g.tiles - g.n_tail);
   k.total_units = (int)g.total_units;
-  k.ws = nullptr; p->ws = nullptr; p->n_tail = (int)g.n_tail;
+  k.ws = nullptr; p->ws = nullptr; p->eff = nullptr; p->n_tail = (int)g.n_tail;
+  {
+    // NOTE: the vectors are snapshots of scale_dev / shift_dev taken now (they are weights: constant after load)
+    const int padded = g.n_tiles * bn;
+    const float om = f16 ? (d->out_mult != 0.f ? d->out_mult : 1.f) : 1.f;
+    cudaError_t e = cudaMalloc(&p->eff, (size_t)2 * padded * sizeof(float));
+    if (e != cudaSuccess) { free(p); return cuda_fail(e, "epilogue vectors", __FILE__, __LINE__); }
+    prep_epilogue_vectors_kernel<<<cdiv(padded, 256), 256>>>(d->scale_dev, d->shift_dev, om, d->cout, padded, p->eff, p->eff + padded);
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { cudaFree(p->eff); free(p); return cuda_fail(e, "prep_epilogue_vectors", __FILE__, __LINE__); }
+    k.scale = p->eff; k.shift = p->eff + padded;
+  }
   if (g.n_tail > 0) {
     cudaError_t e = cudaMalloc(&p->ws, (size_t)g.n_tail * g.splits * BLOCK_M * bn * sizeof(float));
-    if (e != cudaSuccess) { free(p); return cuda_fail(e, "split-tile workspace", __FILE__, __LINE__); }
+    if (e != cudaSuccess) { cudaFree(p->eff); free(p); return cuda_fail(e, "split-tile workspace", __FILE__, __LINE__); }
     k.ws = p->ws;
   }
   p->grid = dim3((unsigned)g.grid, 1, 1);
@@ -1130,5 +1204,6 @@ extern "C" int frcnn_conv_plan_set_trace(frcnn_conv_plan* p, long long* trace_de
 
 extern "C" void frcnn_conv_plan_destroy(frcnn_conv_plan* p) {
   if (p && p->ws) cudaFree(p->ws);
+  if (p && p->eff) cudaFree(p->eff);
   free(p);
 }

@@ -106,6 +106,9 @@ def main():
         return ablate()
     if mode == "ncu":
         one("res_head_c3", 300, 7, 7, 512, 512, 3, impl=0, kpc=4, check=False, reps=2)
+        one("res_head_pw512_2048", 300, 7, 7, 512, 2048, 1, impl=0, kpc=4, check=False, reps=2)
+        one("res_head_pw1024_2048", 300, 7, 7, 1024, 2048, 1, impl=0, kpc=4, check=False, reps=2)
+        one("res_b3_pw1024_256", 1, 38, 50, 1024, 256, 1, impl=0, kpc=4, check=False, reps=2)
         return one("res_b3_c3_256", 1, 38, 50, 256, 256, 3, impl=0, kpc=4, check=False, reps=2)
     print("lib:", N.LIB_PATH, "watchdog:", watchdog() is not None, flush=True)
     t0 = time.time()
