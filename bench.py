@@ -169,65 +169,96 @@ def run_ours(args):
     net.create_architecture("TEST", C, tag="default", anchor_scales=scales, anchor_ratios=(0.5, 1, 2))
     net.load_weights(weights)
     im_info = np.array([H, W, 1.0], np.float32)
-    host_blob = torch.from_numpy(blob).pin_memory()
-    if args.ncu:
+    B = max(1, int(args.batch))
+    from tf_faster_rcnn_b200 import synth
+    blobs = np.concatenate([blob] + [synth.synthetic_blob(H, W, 1000 + 17 * rank + b) for b in range(1, B)], axis=0)
+    host_blob = torch.from_numpy(blobs).pin_memory()
+    scales_b, origs_b = [1.0] * B, [(H, W)] * B
+    if args.ncu or args.layers:
         net.use_cuda_graph = False
-    plan = net.plan_for(H, W)
+    plan = net.plan_for(H, W, B)
     plan.image.copy_(host_blob)
     if args.layers:
-        net.use_cuda_graph = False
-        for _ in range(3):
-            plan.tape.run()
+        # per-launch device times without the CPU launch overhead: each tape step is captured 8x into its own small graph
+        fns = [(lbl, fn) for lbl, fn in plan.tape.steps] + [("detect_post", None)]
+        plan.launch(post=True, detect=True)
         torch.cuda.synchronize()
+        fns[-1] = ("detect_post", plan.post_steps[plan.slot])
         rows = []
-        for lbl, fn in plan.tape.steps:
+        REP = 8
+        for lbl, fn in fns:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                for _ in range(REP):
+                    fn()
+            g.replay(); torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            for _ in range(5):
-                fn()
+            for _ in range(3):
+                g.replay()
             e1.record()
             torch.cuda.synchronize()
-            rows.append((lbl, e0.elapsed_time(e1) * 1000 / 5))
+            rows.append((lbl, e0.elapsed_time(e1) * 1000 / (3 * REP)))
         tot = sum(t for _, t in rows)
-        print("per-launch times (us, warm, back-to-back x5), total %.0f us over %d steps" % (tot, len(rows)))
+        print("per-launch device times (us, warm, 8 back-to-back launches per graph replay), batch %d: total %.0f us = %.0f us per image over %d steps"
+              % (B, tot, tot / B, len(rows)))
         groups = {}
         for lbl, t in rows:
             kind = lbl.split(":")[0]
-            key = kind
+            key_ = kind
             if kind == "conv":
-                key = "conv:" + ("head" if "/block4/" in lbl or "cls_bbox" in lbl or "/fc" in lbl else "rpn" if "/rpn" in lbl else "body")
-            groups[key] = groups.get(key, 0) + t
+                key_ = "conv:" + ("head" if "/block4/" in lbl or "cls_bbox" in lbl or "/fc" in lbl or "Conv2d_1[23]" in lbl else "rpn" if "/rpn" in lbl else "body")
+            groups[key_] = groups.get(key_, 0) + t
         for k, v in sorted(groups.items(), key=lambda kv: -kv[1]):
             print("  %-16s %8.0f us  %5.1f%%" % (k, v, 100 * v / tot))
+        fl = {}
+        for cp, (lbl, _) in zip(plan.tape.conv_plans, [r for r in rows if r[0].startswith("conv:")]):
+            fl[lbl] = cp
         for lbl, t in rows:
-            print("    %-70s %8.1f" % (lbl, t))
+            extra = ""
+            if lbl in fl:
+                extra = "  %7.1f TFLOP/s" % (fl[lbl].flops / t / 1e6)
+            print("    %-70s %8.1f%s" % (lbl, t, extra))
         return
     if args.ncu:
-        plan.launch(1.0, H, W, post=True, detect=True)
+        plan.launch(post=True, detect=True)
         torch.cuda.synchronize()
         torch.cuda.profiler.start()
-        plan.launch(1.0, H, W, post=True, detect=True)
+        plan.launch(post=True, detect=True)
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
-        print("ncu pass done: %d tape steps + 4 post launches" % len(plan.tape.steps))
+        print("ncu pass done: %d tape steps + detect_post, batch %d" % (len(plan.tape.steps), B))
         return
     from tf_faster_rcnn_b200 import parallel
-    rec_bytes = plan.det.numel() * 4 + 4
-    gather = parallel.RecordGather(plan.det, plan.ndet, world)
+    plan.double_buffer = world > 1
+    plan.launch(post=True, detect=True)                      # builds the record buffers
+    torch.cuda.synchronize()
+    rec_bytes = plan.rec.numel() * 4
+    gather = parallel.RecordGather(plan.rec, world) if world > 1 else None
+    step_no = [0]
 
     def step_resident():
-        plan.launch(1.0, H, W, post=True, detect=True)
-        if world > 1:                                   # one all-gather of the fixed-size records per step
-            gather.gather(plan.det, plan.ndet)
+        if gather is not None:
+            gather.before_overwrite(plan.slot ^ 1)             # the gather of two steps ago has read the record buffer reused now
+        plan.launch(post=True, detect=True)
+        if gather is not None:                                # ONE asynchronous all-gather of the fixed-size records per step
+            gather.issue(plan.slot, plan.rec)
+        step_no[0] += 1
 
     def step_e2e():
-        det, _ = net.detect(host_blob, im_info, (H, W))  # H2D blob, graph, post, D2H records (+ sync)
-        if world > 1:
-            gather.gather(plan.det, plan.ndet)
-        return det
+        if gather is not None:
+            gather.before_overwrite(plan.slot ^ 1)
+        dets, _ = net.detect_batch(host_blob, scales_b, origs_b)   # H2D blobs, ONE graph replay, D2H records (+ sync)
+        if gather is not None:
+            gather.issue(plan.slot, plan.rec)
+        step_no[0] += 1
+        return dets
 
     def barrier():
         torch.cuda.synchronize()
+        if gather is not None:
+            gather.before_overwrite(0); gather.before_overwrite(1)
+            torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -238,6 +269,8 @@ def run_ours(args):
         e0.record()
         for _ in range(steps):
             fn()
+        if gather is not None:                                # the last gathers are part of the job
+            gather.before_overwrite(0); gather.before_overwrite(1)
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
@@ -255,58 +288,81 @@ def run_ours(args):
     for _ in range(3):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
-    # dominant kernel (tcgen05 conv/FC GEMM): time only its launches, on the launching stream
+    # dominant kernel (tcgen05 conv/FC GEMM): time only its launches, on the launching stream (one graph of all of them)
     conv_steps = [fn for lbl, fn in plan.tape.steps if lbl.startswith("conv:")]
-
-    def conv_only():
+    cg = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(cg):
         for fn in conv_steps:
             fn()
+
+    def conv_only():
+        cg.replay()
     for _ in range(3):
         conv_only()
     ms_conv = timed(conv_only, args.steps)
     if sampler:
         sampler.stop_flag = True
         sampler.join(timeout=2)
+    # context for the roofline: what the tensor cores of THIS board give a plain library GEMM right now (burst, 8192^3)
+    lib_peaks = {}
+    if rank == 0 and not args.no_lib_peaks:
+        for nm, dt_, tf32 in (("fp16", torch.float16, False), ("tf32", torch.float32, True)):
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            a_ = torch.randn(8192, 8192, device="cuda", dtype=dt_); b_ = torch.randn(8192, 8192, device="cuda", dtype=dt_)
+            best = 0.0
+            for i in range(6):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); torch.matmul(a_, b_); e1.record(); torch.cuda.synchronize()
+                if i:
+                    best = max(best, 2 * 8192.0 ** 3 / (e0.elapsed_time(e1) / 1e3) / 1e12)
+            lib_peaks[nm + "_matmul_tflops_burst"] = best
+            del a_, b_
+        torch.backends.cuda.matmul.allow_tf32 = False
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
     pk, pk_src = peaks()
     n_steps = args.steps
-    value = world * n_steps / (ms / 1000.0)
-    e2e_v = world * n_steps / (ms_e2e / 1000.0)
+    value = world * B * n_steps / (ms / 1000.0)
+    e2e_v = world * B * n_steps / (ms_e2e / 1000.0)
     conv_alg_flops = plan.tape.conv_flops
     conv_tflops = conv_alg_flops * n_steps / (ms_conv / 1000.0) / 1e12
     peak = pk.get("bf16_tflops_sustained", pk.get("bf16_tflops"))
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "r01_conv_traffic.json")
-    if args.net == "res101" and os.path.exists(tp):           # from the committed ncu capture of `bench.py --ncu` (same workload)
+    traffic, traffic_note = None, "no ncu capture of this net / batch committed"
+    tp = os.path.join(ROOT, "profiles", "r02_conv_traffic.json")
+    if os.path.exists(tp):                                    # tools/launch_list_summary.py over the committed ncu launch list of `bench.py --ncu`
         with open(tp) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch_avg")
-    # kernels of this repo launched per image: one per tape step (+1 reduce pass for conv plans with split tiles; the CUB sort
-    # kernels inside the sort step are library code and not counted) + bbox_decode, class_nms, cap_emit after the graph
+            tj = json.load(f).get("%s_b%d" % (args.net, B))
+        if tj:
+            traffic, traffic_note = tj["dram_bytes_per_conv_launch_avg"], tj["note"]
+    # kernels of this repo launched per step: one per tape step (+1 reduce pass for conv plans with split tiles) + class_nms + cap_emit
     try:
         tails = sum(1 for cp in plan.tape.conv_plans if cp.info()["splits"] > 1)
     except Exception:
         tails = 0
-    launches_per_image = len(plan.tape.steps) + tails + 3
+    launches_per_step = len(plan.tape.steps) + tails + 2
     line = {
         "metric": "images/sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": n_steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms / n_steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "tf32x3 (fp32-grade: 3xTF32 tensor-core split, fp32 accumulate)", "data": "synthetic",
-        "config": {"workload": label, "net": args.net, "images_per_step_per_gpu": 1, "parallelism": "image-sharded dp%d" % world,
-                   "l2": "per-image working set (weights hi/lo planes + activations, > 1 GB) exceeds the 126 MB L2; no explicit flush",
-                   "final_nms": "cpu_nms predicate (USE_GPU_NMS=False)", "rpn": "proposal_layer_tf semantics (USE_E2E_TF=True)"},
-        "e2e": {"value": e2e_v, "unit": "images/s", "h2d_bytes_per_step": int(host_blob.numel() * 4), "d2h_bytes_per_step": int(rec_bytes),
-                "ms_per_step": ms_e2e / n_steps},
-        "gpu_launches": launches_per_image * n_steps,
+        "dtype": "f16x3 (fp32-grade: fp16 hi/lo split of both operands, 3 tcgen05 kind::f16 MMAs per product, fp32 accumulate)",
+        "data": "synthetic",
+        "config": {"workload": label, "net": args.net, "images_per_step_per_gpu": B, "parallelism": "image-sharded dp%d" % world,
+                   "l2": "per-step working set (weight planes + activations of %d images, > 1 GB) exceeds the 126 MB L2; no explicit flush" % B,
+                   "final_nms": "cpu_nms predicate (USE_GPU_NMS=False)", "rpn": "proposal_layer_tf semantics (USE_E2E_TF=True)",
+                   "collective": "one async all_gather_into_tensor of the %d-byte record buffer per step" % rec_bytes if world > 1 else "none"},
+        "e2e": {"value": e2e_v, "unit": "images/s", "h2d_bytes_per_step": int(host_blob.numel() * 4 + B * 12), "d2h_bytes_per_step": int(rec_bytes),
+                "ms_per_step": ms_e2e / n_steps, "api": "Network.detect_batch(host blobs) -> per-image detection records on the host"},
+        "gpu_launches": launches_per_step * n_steps,
         "clocks": sampler.summary() if sampler else None,
-        "roofline": {"bound": "tensor", "kernel": "conv_gemm_tf32x3_kernel (all %d conv/FC launches of one image)" % len(conv_steps),
+        "roofline": {"bound": "tensor", "kernel": "conv_gemm_f16x3_kernel (all %d conv/FC launches of one step of %d image(s))" % (len(conv_steps), B),
                      "achieved": conv_tflops, "peak": peak, "unit": "TFLOP/s", "frac": conv_tflops / peak, "traffic": traffic,
-                     "traffic_note": "dram__bytes_read+write per conv launch, averaged over the 106 launches of one image (profiles/r01_conv_traffic.json)",
-                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (%s); 3xTF32 issues 3 TF32 MMAs per product, so its own "
-                                    "ceiling is (TF32 peak)/3 ~ bf16 peak/6" % pk_src,
-                     "algorithmic_gflop_per_image": conv_alg_flops / 1e9, "conv_ms_per_image": ms_conv / n_steps,
+                     "traffic_note": traffic_note,
+                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (%s)" % pk_src,
+                     "scheme_ceiling": {"tflops": peak / 3.0, "frac": conv_tflops / (peak / 3.0),
+                                        "note": "the fp32-grade f16x3 scheme issues 3 fp16 MMAs per product: its own ceiling is peak/3"},
+                     "library_gemm_now": lib_peaks,
+                     "algorithmic_gflop_per_step": conv_alg_flops / 1e9, "conv_ms_per_step": ms_conv / n_steps,
                      "conv_share_of_step": (ms_conv / n_steps) / (ms / n_steps)},
     }
     if not args.no_cpu_baseline and world == 1:
@@ -321,7 +377,7 @@ def run_ours(args):
             cpu_reference_step(key, weights, blob, im_info, C, scales, post)
         dt = (time.perf_counter() - t1) / nrep
         line["cpu_baseline"] = {"value": 1.0 / dt, "unit": "images/s", "cores": _t.get_num_threads(), "kind": "port",
-                                "sample": "%d image(s) of the same workload after 1 warm-up" % nrep}
+                                "sample": "%d image(s) of the same workload after 1 warm-up (an untuned CPU port, not TF1-Eigen)" % nrep}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -335,6 +391,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--net", default="res101", choices=sorted(NETS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-lib-peaks", action="store_true", help="skip the two 8192^3 library matmuls timed for context after the run")
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("FRCNN_BENCH_BATCH", "4")),
+                    help="images per GPU per step (one graph replay); 1 = the reference's batch size")
     ap.add_argument("--layers", action="store_true", help="print a per-launch CUDA-event timing table of one image (eager, warm) and exit")
     ap.add_argument("--ncu", action="store_true", help="profiling aid: eager launches (no CUDA graph), one warm-up image, then ONE image "
                     "between cudaProfilerStart/Stop (run under `ncu --profile-from-start off`); prints no bench line")

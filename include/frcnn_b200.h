@@ -150,29 +150,35 @@ int frcnn_spatial_mean(const float* in_dev, float* out_dev, int r, int hw, int c
 int frcnn_preprocess(const unsigned char* img_dev, int h0, int w0, const double* means3, double fx, double fy,
                      float* blob_dev, int H, int W, void* stream);
 
+/* ---- (4) proposal / detection stages.  Every stage takes `batch` images of one blob shape (the reference is batch 1,
+ * lib/nets/network.py:388; batch > 1 is the throughput extension of SURVEY.md 8(f) rank 4): per-image arrays are
+ * concatenated image-major, RoI rows carry their image index in column 0 exactly like crop_and_resize's box_ind. ---- */
+
 /* RPN: 2-way softmax (fg prob), anchor generation, bbox_transform_inv, clip -- proposal_layer.py:62-69.
- * rpn_out_dev: [hw, ld] rows with the 2A class logits at column 0 and the 4A deltas at column delta_col
+ * rpn_out_dev: [batch*hw, ld] rows with the 2A class logits at column 0 and the 4A deltas at column delta_col
  * (delta_col % 4 == 0, ld % 4 == 0: the fused 1x1 RPN head writes both).
- * base_anchors_dev [A,4].  scores_dev [hw*A], props_dev [hw*A,4] in (h,w,a) order. */
+ * base_anchors_dev [A,4].  scores_dev [batch*hw*A], props_dev [batch*hw*A,4] in (image,h,w,a) order. */
 int frcnn_rpn_decode(const float* rpn_out_dev, int ld, int delta_col, const float* base_anchors_dev, int num_anchors,
-                     int fh, int fw, int feat_stride, float im_h, float im_w, float* scores_dev,
+                     int batch, int fh, int fw, int feat_stride, float im_h, float im_w, float* scores_dev,
                      float* props_dev, void* stream);
-/* stable descending sort of n fp32 keys (ties: lower index first) -> order_dev int32[n].
- * workspace: frcnn_sort_workspace_bytes(n) bytes */
+/* stable descending sort of `batch` segments of n fp32 keys each (ties: lower index first) -> order_dev int32[batch*n],
+ * indices LOCAL to the segment; one thread-block cluster per segment, n <= 90 112.  The workspace arguments are kept
+ * from the r01 (CUB based) signature and may be NULL / 0. */
 size_t frcnn_sort_workspace_bytes(int n);
-int frcnn_sort_desc(const float* keys_dev, int n, int* order_dev, float* sorted_keys_dev, void* workspace_dev,
+int frcnn_sort_desc(const float* keys_dev, int n, int batch, int* order_dev, float* sorted_keys_dev, void* workspace_dev,
                     size_t workspace_bytes, void* stream);
-/* proposal selection (proposal_layer_tf / proposal_layer / proposal_top_layer): walk `order`, greedy NMS
+/* proposal selection (proposal_layer_tf / proposal_layer / proposal_top_layer), per image: walk `order`, greedy NMS
  * with `flags` over the first `pre_nms_top_n` (<=0: all) candidates, stop at post_nms_top_n.  thresh < 0
- * means no NMS (TEST.MODE='top').  rois_dev [post_nms_top_n,5] = (0,x1,y1,x2,y2), zero padded;
- * roi_scores_dev [post_nms_top_n]; keep_dev int32 indices into props; num_dev int32 count. */
-int frcnn_proposals(const float* props_dev, const float* scores_dev, const int* order_dev, int n,
+ * means no NMS (TEST.MODE='top').  props/scores/order: [batch][n].  rois_dev [batch*post_nms_top_n,5] =
+ * (image,x1,y1,x2,y2), zero padded per image; roi_scores_dev [batch*post_nms_top_n]; keep_dev int32 segment-local
+ * indices into props; num_dev int32[batch] counts. */
+int frcnn_proposals(const float* props_dev, const float* scores_dev, const int* order_dev, int n, int batch,
                     int pre_nms_top_n, int post_nms_top_n, float thresh, unsigned flags, float* rois_dev,
                     float* roi_scores_dev, int* keep_dev, int* num_dev, void* stream);
 /* tf.image.crop_and_resize on the stride-16 feature map + optional 2x2 max pool (network.py:141-157,
- * resnet_v1.py:55-76).  rois_dev [r,5] blob-scale pixels.  pooled = 7; pre_pool 0: direct 7x7,
- * 1: 14x14 then 2x2/2 max.  out [r,7,7,c] */
-int frcnn_crop_pool(const float* feat_dev, int fh, int fw, int c, const float* rois_dev, int r, int pooled,
+ * resnet_v1.py:55-76).  feat_dev [batch,fh,fw,c]; rois_dev [r,5] = (image index, blob-scale pixels).  pooled = 7;
+ * pre_pool 0: direct 7x7, 1: 14x14 then 2x2/2 max.  out [r,7,7,c] */
+int frcnn_crop_pool(const float* feat_dev, int batch, int fh, int fw, int c, const float* rois_dev, int r, int pooled,
                     int pre_pool, float* out_dev, void* stream);
 /* split the fused [r, ld] head GEMM output (cls logits at col 0, 4C deltas at col C):
  * cls_score [r,C], cls_prob = softmax, bbox_pred = delta*stds + means (network.py:361-378,428-432) */
@@ -180,17 +186,24 @@ int frcnn_cls_finish(const float* head_out_dev, int ld, int r, int num_classes, 
                      const float* means4, float* cls_score_dev, float* cls_prob_dev, float* bbox_pred_dev,
                      void* stream);
 /* im_detect tail: boxes = rois[:,1:5]/scale; bbox_transform_inv; one-sided clip to the ORIGINAL image
- * (lib/model/test.py:95-102,67-77).  pred_boxes_dev [r,4C] */
-int frcnn_bbox_decode(const float* rois_dev, const float* bbox_pred_dev, int r, int num_classes,
-                      float im_scale, int orig_h, int orig_w, float* pred_boxes_dev, void* stream);
-/* test_net tail (lib/model/test.py:162-180): per class j>=1: score > thresh, NMS(flags, nms_thresh), then the
- * max_per_image cap over all classes.  num_rois_dev: int32 valid-row count (rows beyond are ignored).
- * det_dev [max_det,6] = (x1,y1,x2,y2,score,class) sorted by (class, descending score); ndet_dev int32.
- * keep_dev [C, r] int32 roi indices per class (after the cap), keep_cnt_dev [C]; keep_score_dev [C, r] scratch. */
-int frcnn_detect_post(const float* cls_prob_dev, const float* pred_boxes_dev, const int* num_rois_dev, int r,
+ * (lib/model/test.py:95-102,67-77).  im_meta_dev [batch,3] fp32 = (im_scale, orig_h, orig_w) per image, read on the
+ * device (the launch is CUDA-graph capturable: the host only rewrites the 12 bytes).  pred_boxes_dev [r,4C] */
+int frcnn_bbox_decode(const float* rois_dev, const float* bbox_pred_dev, int r, int num_classes, int batch,
+                      const float* im_meta_dev, float* pred_boxes_dev, void* stream);
+/* test_net tail (lib/model/test.py:162-180), per image: per class j>=1: score > thresh, NMS(flags, nms_thresh), then the
+ * max_per_image cap over all classes.  r = RoI rows per image (<= 8192; above 1024 -- TEST.MODE='top' with
+ * RPN_TOP_N=5000 -- the kept sets live in `workspace_dev`, frcnn_detect_post_workspace_bytes(r, C, batch) bytes, else the
+ * workspace may be NULL).  num_rois_dev: int32[batch] valid-row counts.  det_dev [batch,max_det,6] =
+ * (x1,y1,x2,y2,score,class) sorted by (class, descending score); ndet_dev int32[batch] = the number of detections of
+ * the image, which EXCEEDS max_det when the records did not fit (the caller must treat that as an error).
+ * record_stride (4-byte words; 0 = dense): distance between consecutive images in BOTH det_dev and ndet_dev, so that a
+ * caller can interleave count and rows into one fixed-size record per image (the multi-GPU all-gather payload).
+ * keep_dev [batch,C,r] int32 roi indices per class (after the cap), keep_cnt_dev [batch,C]; keep_score_dev [batch,C,r]. */
+size_t frcnn_detect_post_workspace_bytes(int r, int num_classes, int batch);
+int frcnn_detect_post(const float* cls_prob_dev, const float* pred_boxes_dev, const int* num_rois_dev, int r, int batch,
                       int num_classes, float score_thresh, float nms_thresh, unsigned flags,
-                      int max_per_image, int max_det, float* det_dev, int* ndet_dev, int* keep_dev,
-                      int* keep_cnt_dev, float* keep_score_dev, void* stream);
+                      int max_per_image, int max_det, float* det_dev, int* ndet_dev, int record_stride, int* keep_dev,
+                      int* keep_cnt_dev, float* keep_score_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

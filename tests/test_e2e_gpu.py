@@ -38,6 +38,41 @@ def relerr(a, b):
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
 
 
+def compare_detections(det, want_per_class, tol=0.05):
+    """Match final detections (rows x1,y1,x2,y2,score,class) with the oracle's per-class lists: a detection is matched to the
+    closest oracle box of its class when every coordinate agrees within `tol` px.  Unmatched rows on either side are near-tie
+    flips of the two sorts / greedy NMS passes upstream (different fp32 summation orders), counted, not hidden."""
+    n_want = int(sum(d.shape[0] for d in want_per_class))
+    matched, box_err, score_err = 0, 0.0, 0.0
+    cls = det[:, 5].astype(np.int64) if det.shape[0] else np.zeros(0, np.int64)
+    for j, w in enumerate(want_per_class):
+        g = det[cls == j]
+        if not g.shape[0] or not w.shape[0]:
+            continue
+        d = np.abs(g[:, None, :4] - w[None, :, :4]).max(axis=2)
+        used = set()
+        for i in range(g.shape[0]):
+            k = int(np.argmin(d[i]))
+            if d[i, k] <= tol and k not in used:
+                used.add(k); matched += 1
+                box_err = max(box_err, float(d[i, k])); score_err = max(score_err, float(abs(g[i, 4] - w[k, 4])))
+    return dict(n_got=int(det.shape[0]), n_want=n_want, matched=matched, box_err=box_err, score_err=score_err)
+
+
+def fmt_report(r):
+    return "detections gpu %d oracle %d matched %d (flips: %d gpu-only, %d oracle-only) | matched: box max %.2e px, score max %.2e" % (
+        r["n_got"], r["n_want"], r["matched"], r["n_got"] - r["matched"], r["n_want"] - r["matched"], r["box_err"], r["score_err"])
+
+
+def parity_log(line):
+    """Append to gpurun_out/r02_parity.log when run on the GPU box (copied into profiles/r02_parity.md afterwards)."""
+    import os
+    d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(d):
+        with open(os.path.join(d, "r02_parity.log"), "a") as f:
+            f.write(line.rstrip() + "\n")
+
+
 @pytest.mark.parametrize("net_name,C,scales,hw", [
     ("vgg16", 21, (8, 16, 32), (300, 400)),
     ("res101", 81, (4, 8, 16, 32), (600, 800)),
@@ -71,9 +106,9 @@ def test_test_image_matches_oracle(cuda, net_name, C, scales, hw):
           (net_name, hw[0], hw[1], e_feat, e_rpn_cls, e_rpn_box, e_scores, e_props, same_set, len(common), len(st["roi_keep"]),
            e_prob, e_bbox, e_rois, plan.tape.flops / 1e9))
     assert e_feat < 2e-5 and e_rpn_cls < 2e-5 and e_rpn_box < 5e-5
-    assert e_scores < 2e-5 and e_props < 2e-2        # end-to-end drift: exp(dw)*w amplifies a 1e-5 delta error by the box size
+    assert e_scores < 2e-5 and e_props < 5e-3        # end-to-end drift: exp(dw)*w amplifies a 1e-5 delta error by the box size
     assert len(common) >= 0.97 * len(st["roi_keep"])
-    assert e_prob < 1e-4 and e_bbox < 1e-4 and e_rois < 2e-2
+    assert e_prob < 1e-4 and e_bbox < 1e-4 and e_rois < 5e-3
 
 
 def test_im_detect_and_fused_detect(cuda):
@@ -132,13 +167,21 @@ def _run_modes(net_name, C, scales, hw, cfg_updates, oracle_opts):
 def test_top_mode_end_to_end(cuda):
     """TEST.MODE='top' (proposal_top_layer_tf): 5000 RoIs by score, no NMS -- through the whole net."""
     net, st, (cls_score, cls_prob, bbox_pred, rois) = _run_modes(
-        "mobile", 21, (8, 16, 32), (224, 320), {"TEST.MODE": "top", "TEST.RPN_TOP_N": 1000}, dict(test_mode="top", rpn_top_n=1000))
-    assert rois.shape == (1000, 5) and st["rois"].shape == (1000, 5)
-    plan = net.plan_for(224, 320)
+        "mobile", 21, (8, 16, 32), (320, 480), {"TEST.MODE": "top"}, dict(test_mode="top"))      # RPN_TOP_N = 5000 (config.py:208)
+    assert rois.shape == (5000, 5) and st["rois"].shape == (5000, 5)
+    plan = net.plan_for(320, 480)
     keep = plan.roi_keep.cpu().numpy()
     common, ia, ib = np.intersect1d(keep, st["roi_keep"], return_indices=True)
-    assert len(common) >= 990
+    assert len(common) >= 4950
     assert np.abs(cls_prob[ia] - st["cls_prob"][ib]).max() < 1e-4 and np.abs(bbox_pred[ia] - st["bbox_pred"][ib]).max() < 1e-4
+    # ... and through the fused test_net tail (5000 RoIs per class list: kept sets in the global workspace)
+    blob = synth.synthetic_blob(320, 480)
+    det, _ = net.detect(blob, np.array([320, 480, 1.0], F), (320, 480))
+    scores, boxes = P.im_detect_post(st["rois"], st["cls_prob"], st["bbox_pred"], 1.0, 320, 480)
+    want = P.test_net_post(scores, boxes, P.opts())
+    rep = compare_detections(det, want)
+    print("\n[top-mode 5000] " + fmt_report(rep))
+    assert rep["matched"] >= 0.9 * rep["n_want"] and rep["box_err"] < 2e-2 and rep["score_err"] < 1e-4
 
 
 @pytest.mark.parametrize("gpu_pred", [False, True])
@@ -173,6 +216,7 @@ def test_shape_cache_and_repeatability(cuda):
     r2 = net.test_image(None, b, np.array([240, 272, 1.0], F))
     r3 = net.test_image(None, a, np.array([208, 320, 1.0], F))
     assert len(net._plans) == 2
+    assert list(net._plans)[-1] == (208, 320, 1)      # most recently used last
     for x, y in zip(r1, r3):
         assert np.array_equal(x, y)
     assert r2[3].shape[1] == 5
@@ -191,3 +235,83 @@ def test_im_detect_with_device_preprocess(cuda):
     finally:
         MT.DEVICE_PREPROCESS = False
     assert s0.shape == s1.shape and np.abs(s0 - s1).max() < 1e-3 and np.abs(b0 - b1).max() < 0.5
+
+
+FULL_CONFIGS = [
+    # (label, net, classes, anchor scales, blob H x W, cfg updates, oracle option updates, end-to-end box bound in px)
+    # The box bound is 2x the measured end-to-end drift (profiles/r02_parity.md): two fp32 summation orders upstream, amplified by
+    # exp(dw) * w -- it grows with the largest anchor (724 px wide at scale 32, 1448 px with the 800 px config's anchors).
+    ("cfg2 ResNet-101 COCO 600x800, 300 proposals", "res101", 81, (4, 8, 16, 32), (600, 800), {}, {}, 5e-3),
+    ("cfg1/3 VGG16 VOC 600x800, 300 proposals", "vgg16", 21, (8, 16, 32), (600, 800), {}, {}, 9e-3),
+    ("cfg4 MobileNet-v1 COCO 600x800", "mobile", 81, (4, 8, 16, 32), (600, 800), {}, {}, 4e-3),
+    ("cfg5 ResNet-152 800x1067, A=15, 1000 proposals", "res152", 81, (2, 4, 8, 16, 32), (800, 1067),
+     {"TEST.RPN_POST_NMS_TOP_N": 1000}, dict(rpn_post_nms_top_n=1000), 2.6e-2),
+]
+
+
+@pytest.mark.parametrize("label,net_name,C,scales,hw,cfg_updates,oo,box_tol", FULL_CONFIGS, ids=[c[1] for c in FULL_CONFIGS])
+def test_full_size_detections_match_oracle(cuda, label, net_name, C, scales, hw, cfg_updates, oo, box_tol):
+    """BASELINE.json configs at their FULL shapes: Network.detect() (one graph replay: backbone .. per-class NMS .. cap) against
+    the oracle's OWN chain test_image -> im_detect_post -> test_net_post -- nothing of the GPU run is fed to the oracle."""
+    net, st, (cls_score, cls_prob, bbox_pred, rois) = _run_modes(net_name, C, scales, hw, cfg_updates, oo)
+    plan = net.plan_for(*hw)
+    keep = plan.roi_keep.cpu().numpy()[:rois.shape[0]]
+    common, ia, ib = np.intersect1d(keep, st["roi_keep"], return_indices=True)
+    e_props = float(np.abs(plan.rpn_props.cpu().numpy() - st["rpn_props"]).max())
+    e_rois = float(np.abs(rois[ia] - st["rois"][ib]).max())
+    e_prob = float(np.abs(cls_prob[ia] - st["cls_prob"][ib]).max())
+    e_bbox = float(np.abs(bbox_pred[ia] - st["bbox_pred"][ib]).max())
+    same_order = np.array_equal(keep, st["roi_keep"])
+    blob = synth.synthetic_blob(*hw)
+    det, _ = net.detect(blob, np.array([hw[0], hw[1], 1.0], F), hw)
+    scores, boxes = P.im_detect_post(st["rois"], st["cls_prob"], st["bbox_pred"], 1.0, hw[0], hw[1])
+    want = P.test_net_post(scores, boxes, P.opts(anchor_scales=scales, **oo))
+    rep = compare_detections(det, want)
+    line = ("[%s] RoIs: gpu %d oracle %d common %d identical-order=%s | proposals abs %.2e px, common RoIs abs %.2e px, cls_prob abs %.2e, "
+            "bbox_pred abs %.2e | %s" % (label, rois.shape[0], st["rois"].shape[0], len(common), same_order, e_props, e_rois, e_prob, e_bbox,
+                                       fmt_report(rep)))
+    print("\n" + line)
+    parity_log(line)
+    assert len(common) >= 0.97 * len(st["roi_keep"])
+    assert e_prob < 1e-4 and e_bbox < 1e-4                       # north-star tolerance on the RoIs both sides selected
+    assert e_rois < box_tol and e_props < box_tol
+    assert rep["matched"] >= 0.95 * rep["n_want"] and rep["score_err"] < 1e-4 and rep["box_err"] < box_tol
+
+
+def test_detect_batch_matches_oracle_per_image(cuda):
+    """Batch of 3 different images of one blob shape through ONE graph replay: every image's records match the oracle run on
+    that image alone (per-image scale / original size are read from the device meta rows)."""
+    net, w = build("res50", 21, (8, 16, 32))
+    hw = (224, 304)
+    blobs = np.concatenate([synth.synthetic_blob(hw[0], hw[1], seed) for seed in (1, 2, 3)], axis=0)
+    scales = [1.0, 1.25, 0.8]
+    orig = [(224, 304), (179, 243), (280, 380)]
+    dets, plan = net.detect_batch(blobs, scales, orig)
+    assert plan.batch == 3 and len(dets) == 3
+    o = P.opts()
+    for b in range(3):
+        st = P.test_image("res50", w, blobs[b:b + 1], np.array([hw[0], hw[1], scales[b]], F), 21, o)
+        scores, boxes = P.im_detect_post(st["rois"], st["cls_prob"], st["bbox_pred"], scales[b], orig[b][0], orig[b][1])
+        want = P.test_net_post(scores, boxes, o)
+        rep = compare_detections(dets[b], want)
+        line = "[batch-of-3 image %d, res50 224x304] %s" % (b, fmt_report(rep))
+        print("\n" + line); parity_log(line)
+        assert rep["matched"] >= 0.9 * rep["n_want"] and rep["score_err"] < 1e-4 and rep["box_err"] < 5e-3
+    # the same images one at a time give the same records up to the summation order of the split-K layers
+    for b in range(3):
+        single, _ = net.detect(blobs[b:b + 1], np.array([hw[0], hw[1], scales[b]], F), orig[b])
+        rep = compare_detections(dets[b], [single[single[:, 5] == j, :5] for j in range(21)])
+        assert rep["matched"] >= 0.95 * max(single.shape[0], 1) and rep["score_err"] < 1e-4
+
+
+def test_plan_cache_is_bounded(cuda):
+    """the per-shape plan cache is an LRU (hundreds of distinct blob shapes in a dataset must not exhaust HBM)."""
+    net, w = build("res50", 21, (8, 16, 32))
+    net.MAX_PLANS = 2
+    shapes = [(208, 320), (224, 272), (240, 256), (208, 320)]
+    outs = []
+    for i, (h, wd) in enumerate(shapes):
+        outs.append(net.test_image(None, synth.synthetic_blob(h, wd, 1), np.array([h, wd, 1.0], F)))
+        assert len(net._plans) <= 2
+    for x, y in zip(outs[0], outs[3]):           # evicted and rebuilt: same results
+        assert np.array_equal(x, y)

@@ -153,20 +153,29 @@ GLOO_WORKER = textwrap.dedent("""
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     dist.init_process_group("gloo", rank=rank, world_size=world)
     num_images, C, max_det = 5, 4, 8
+    H = PP.REC_HEADER
     all_boxes = [[[] for _ in range(num_images)] for _ in range(C)]
-    det = torch.zeros(max_det, 6); ndet = torch.zeros(1, dtype=torch.int32)
-    g = PP.RecordGather(det, ndet, world)
+    recs = [torch.zeros(H + max_det * 6), torch.zeros(H + max_det * 6)]      # the producer alternates between two record buffers
+    g = PP.RecordGather(recs[0], world)
     mine = PP.shard_indices(num_images, rank, world)
-    for step in range(PP.steps_for(num_images, world)):
-        det.zero_(); ndet.zero_()
+    nsteps = PP.steps_for(num_images, world)
+    for step in range(nsteps):
+        slot = step & 1
+        g.before_overwrite(slot)
+        rec = recs[slot]
+        rec.zero_()
         if step < len(mine):
             img = mine[step]
             n = 1 + img %% 3
+            rows = rec[H:].view(max_det, 6)
             for k in range(n):
-                det[k] = torch.tensor([img, k, img + 10, k + 10, 0.9 - 0.1 * k, 1 + (img + k) %% (C - 1)], dtype=torch.float32)
-            ndet[0] = n
-        d, nn = g.gather(det, ndet)
-        PP.records_to_all_boxes(all_boxes, step, world, d, nn, num_images)
+                rows[k] = torch.tensor([img, k, img + 10, k + 10, 0.9 - 0.1 * k, 1 + (img + k) %% (C - 1)], dtype=torch.float32)
+            rec.view(torch.int32)[0] = n
+        g.issue(slot, rec)                                   # ONE collective per step, asynchronous
+        if step > 0:
+            PP.records_to_all_boxes(all_boxes, step - 1, world, g.result(slot ^ 1), num_images)
+    PP.records_to_all_boxes(all_boxes, nsteps - 1, world, g.result((nsteps - 1) & 1), num_images)
+    assert g.collectives == nsteps, g.collectives
     tot = sum(len(all_boxes[j][i]) for j in range(1, C) for i in range(num_images))
     assert tot == sum(1 + i %% 3 for i in range(num_images)), tot
     for i in range(num_images):
@@ -203,12 +212,19 @@ SHARDED_WORKER = textwrap.dedent("""
         num_classes = 4
         def __init__(self, n): self.image_index = list(range(n))
 
+    from tf_faster_rcnn_b200.parallel import REC_HEADER as H
+    bufs = [torch.zeros(H + 12 * 6), torch.zeros(H + 12 * 6)]
+    turn = [0]
+
     def fake(i, cap=12):            # a deterministic stand-in for the device path: records depend on the image only
         n = (i * 5) %% 7
-        det = torch.zeros(cap, 6)
+        rec = bufs[turn[0] & 1]; turn[0] += 1        # like ShapePlan: consecutive records alternate between two buffers
+        rec.zero_()
+        rows = rec[H:].view(cap, 6)
         for k in range(n):
-            det[k] = torch.tensor([i, k, i + 20, k + 20, 1.0 - 0.1 * k, 1 + (i + k) %% 3], dtype=torch.float32)
-        return det, torch.tensor([n], dtype=torch.int32)
+            rows[k] = torch.tensor([i, k, i + 20, k + 20, 1.0 - 0.1 * k, 1 + (i + k) %% 3], dtype=torch.float32)
+        rec.view(torch.int32)[0] = n
+        return rec
 
     out = {}
     for n_images in (5, 1, 0, 4):

@@ -145,12 +145,15 @@ def test_rpn_decode(cuda, scales):
 def test_sort_desc_stable(cuda):
     from tf_faster_rcnn_b200 import ops
     rng = np.random.default_rng(3)
-    for n in (1, 2, 255, 256, 257, 22800, 50250):
+    for n in (1, 2, 7, 8, 9, 255, 256, 257, 8191, 8192, 8193, 22800, 50250, 90112):
         keys = rng.random(n).astype(F)
         keys[rng.integers(0, n, n // 3)] = F(0.5)      # many exact ties
+        if n > 100:
+            keys[:40] = (rng.standard_normal(40) * 1e3).astype(F)       # negative / large keys, +-0, denormals: the total order
+            keys[40:44] = [0.0, -0.0, 1e-40, -1e-40]
         order = torch.empty(n, dtype=torch.int32, device="cuda")
         sk = torch.empty(n, dtype=torch.float32, device="cuda")
-        ops.sort_desc(dev(keys), order, sk, ops.sort_workspace(n))
+        ops.sort_desc(dev(keys), order, sk)
         assert np.array_equal(order.cpu().numpy(), ONMS.argsort_desc(keys)), n
 
 
@@ -173,7 +176,7 @@ def test_proposals_tf_mode(cuda, n, post):
     want_rois, want_sc, want_keep = P.proposals_e2e_tf(scores, props, P.opts(rpn_post_nms_top_n=post))
     order = torch.empty(n, dtype=torch.int32, device="cuda"); sk = torch.empty(n, dtype=torch.float32, device="cuda")
     pd, sd = dev(props), dev(scores)
-    ops.sort_desc(sd, order, sk, ops.sort_workspace(n))
+    ops.sort_desc(sd, order, sk)
     rois = torch.empty((post, 5), dtype=torch.float32, device="cuda"); rs = torch.empty(post, dtype=torch.float32, device="cuda")
     keep = torch.empty(post, dtype=torch.int32, device="cuda"); num = torch.zeros(1, dtype=torch.int32, device="cuda")
     ops.proposals(pd, sd, order, 0, post, 0.7, N.NMS_MODE_TF, rois, rs, keep, num)
@@ -196,7 +199,7 @@ def test_proposals_numpy_mode_and_top(cuda, gpu_pred):
     want_rois, _, want_keep = P.proposals_numpy(scores, props, o)
     order = torch.empty(n, dtype=torch.int32, device="cuda"); sk = torch.empty(n, dtype=torch.float32, device="cuda")
     pd, sd = dev(props), dev(scores)
-    ops.sort_desc(sd, order, sk, ops.sort_workspace(n))
+    ops.sort_desc(sd, order, sk)
     rois = torch.empty((300, 5), dtype=torch.float32, device="cuda"); rs = torch.empty(300, dtype=torch.float32, device="cuda")
     keep = torch.empty(300, dtype=torch.int32, device="cuda"); num = torch.zeros(1, dtype=torch.int32, device="cuda")
     flags = N.NMS_MODE_GPU_NMS if gpu_pred else N.NMS_MODE_CPU_NMS
@@ -235,7 +238,7 @@ def test_cls_finish_and_bbox_decode(cuda):
     scale = 1.6
     _, want_pred = P.im_detect_post(rois, want_prob, want_bbox, scale, 375, 500)
     pred = torch.empty((R, 4 * Cc), dtype=torch.float32, device="cuda")
-    ops.bbox_decode(dev(rois), dev(want_bbox), Cc, scale, 375, 500, pred)
+    ops.bbox_decode(dev(rois), dev(want_bbox), Cc, ops.im_meta_tensor([(scale, 375, 500)]), pred)
     assert np.abs(pred.cpu().numpy() - want_pred).max() < 1e-4      # north-star box tolerance
 
 
@@ -342,3 +345,93 @@ def test_device_preprocess_matches_opencv(cuda, hw):
     err = np.abs(blob.cpu().numpy() - want).max()
     print("\n[preprocess %dx%d -> %dx%d] max abs diff vs OpenCV %.2e" % (hw[0], hw[1], H, W, err))
     assert err < 1e-4
+
+
+def test_sort_desc_segments(cuda):
+    """batch > 1: every segment is sorted on its own cluster, indices are segment-local."""
+    from tf_faster_rcnn_b200 import ops
+    rng = np.random.default_rng(5)
+    B, n = 3, 17100
+    keys = rng.random((B, n)).astype(F)
+    keys[1, ::3] = F(0.25)
+    order = torch.empty(B * n, dtype=torch.int32, device="cuda"); sk = torch.empty(B * n, dtype=torch.float32, device="cuda")
+    ops.sort_desc(dev(keys.reshape(-1)), order, sk, batch=B)
+    o = order.cpu().numpy().reshape(B, n); k = sk.cpu().numpy().reshape(B, n)
+    for b in range(B):
+        want = ONMS.argsort_desc(keys[b])
+        assert np.array_equal(o[b], want)
+        assert np.array_equal(k[b], keys[b][want])
+
+
+def test_batched_proposal_stages_match_per_image(cuda):
+    """rpn_decode -> sort -> proposals -> crop_pool -> bbox_decode -> detect_post on a batch of 3 images equal, bit for bit,
+    the same stages run image by image (the per-image arrays are only concatenated; RoI column 0 selects the image)."""
+    from tf_faster_rcnn_b200 import ops, _native as N
+    rng = np.random.default_rng(77)
+    B, A, fh, fw, Cc, R = 3, 9, 38, 50, 21, 300
+    n = fh * fw * A
+    dcol = (2 * A + 3) // 4 * 4; ld = (dcol + 4 * A + 3) // 4 * 4
+    fused = np.zeros((B, fh * fw, ld), F)
+    fused[..., :2 * A] = (rng.standard_normal((B, fh * fw, 2 * A)) * 2).astype(F)
+    fused[..., dcol:dcol + 4 * A] = (rng.standard_normal((B, fh * fw, 4 * A)) * 0.3).astype(F)
+    base = dev(OA.base_anchors(ratios=(0.5, 1, 2), scales=(8, 16, 32)).astype(F))
+    feat = rng.standard_normal((B, fh, fw, 64)).astype(F)
+    meta = [(1.6, 375, 500), (1.2, 500, 667), (2.0, 300, 400)]
+    probs = L.softmax_lastdim((rng.standard_normal((B * R, Cc)) * 2).astype(F))
+    deltas = (rng.standard_normal((B * R, 4 * Cc)) * 0.2).astype(F)
+
+    def run(b_lo, b_hi):
+        nb = b_hi - b_lo
+        scores = torch.empty(nb * n, dtype=torch.float32, device="cuda"); props = torch.empty((nb * n, 4), dtype=torch.float32, device="cuda")
+        ops.rpn_decode(dev(fused[b_lo:b_hi].reshape(nb * fh * fw, ld)), dcol, base, A, fh, fw, 600.0, 800.0, scores, props, batch=nb)
+        order = torch.empty(nb * n, dtype=torch.int32, device="cuda"); sk = torch.empty(nb * n, dtype=torch.float32, device="cuda")
+        ops.sort_desc(scores, order, sk, batch=nb)
+        rois = torch.empty((nb * R, 5), dtype=torch.float32, device="cuda"); rs = torch.empty(nb * R, dtype=torch.float32, device="cuda")
+        keep = torch.empty(nb * R, dtype=torch.int32, device="cuda"); num = torch.zeros(nb, dtype=torch.int32, device="cuda")
+        ops.proposals(props, scores, order, 0, R, 0.7, N.NMS_MODE_TF, rois, rs, keep, num, batch=nb)
+        pool = torch.empty((nb * R, 7, 7, 64), dtype=torch.float32, device="cuda")
+        ops.crop_pool(dev(feat[b_lo:b_hi]), rois, 7, 0, pool)
+        pred = torch.empty((nb * R, 4 * Cc), dtype=torch.float32, device="cuda")
+        ops.bbox_decode(rois, dev(deltas[b_lo * R:b_hi * R]), Cc, ops.im_meta_tensor(meta[b_lo:b_hi]), pred)
+        det = torch.zeros((nb, 256, 6), dtype=torch.float32, device="cuda"); ndet = torch.zeros(nb, dtype=torch.int32, device="cuda")
+        kp = torch.empty((nb, Cc, R), dtype=torch.int32, device="cuda"); cnt = torch.empty((nb, Cc), dtype=torch.int32, device="cuda")
+        ks = torch.empty((nb, Cc, R), dtype=torch.float32, device="cuda")
+        ops.detect_post(dev(probs[b_lo * R:b_hi * R]), pred, num, Cc, 0.0, float(ONMS.thresh_f32(0.3, True)), N.NMS_MODE_CPU_NMS, 100,
+                        det, ndet, kp, cnt, ks, batch=nb)
+        torch.cuda.synchronize()
+        r = rois.cpu().numpy().reshape(nb, R, 5).copy()
+        r[:, :, 0] = 0
+        return (r, num.cpu().numpy(), pool.cpu().numpy().reshape(nb, R, 7, 7, 64), pred.cpu().numpy().reshape(nb, R, -1),
+                det.cpu().numpy(), ndet.cpu().numpy(), rois.cpu().numpy().reshape(nb, R, 5)[:, :, 0])
+    whole = run(0, B)
+    for b in range(B):
+        one = run(b, b + 1)
+        for i in range(6):
+            assert np.array_equal(whole[i][b], one[i][0]), (b, i)
+        k = int(whole[1][b])
+        assert k > 50 and (whole[6][b][:k] == b).all()          # the RoI rows carry their image index
+        nd = int(whole[5][b])
+        assert 0 < nd <= 256
+
+
+def test_detect_post_top_mode_5000_rois(cuda):
+    """TEST.MODE='top': RPN_TOP_N = 5000 RoIs per image (lib/model/config.py:208) through the fused post path -- the kept
+    sets live in the global-memory workspace; records bit-exact against the oracle."""
+    from tf_faster_rcnn_b200 import ops, _native as N
+    rng = np.random.default_rng(5000)
+    R, Cc = 5000, 21
+    probs = L.softmax_lastdim((rng.standard_normal((R, Cc)) * 2).astype(F))
+    centers = rand_boxes(rng, R, 500.0, (20, 200))
+    pred = np.repeat(centers[:, None, :], Cc, axis=1) + rng.uniform(-15, 15, (R, Cc, 4)).astype(F)
+    pred = np.round(pred.reshape(R, 4 * Cc)).astype(F)
+    want = P.test_net_post(probs, pred, P.opts())
+    det = torch.zeros((2048, 6), dtype=torch.float32, device="cuda"); ndet = torch.zeros(1, dtype=torch.int32, device="cuda")
+    keep = torch.empty((Cc, R), dtype=torch.int32, device="cuda"); cnt = torch.empty(Cc, dtype=torch.int32, device="cuda")
+    ks = torch.empty((Cc, R), dtype=torch.float32, device="cuda")
+    nr = torch.tensor([R], dtype=torch.int32, device="cuda")
+    ops.detect_post(dev(probs), dev(pred), nr, Cc, 0.0, float(ONMS.thresh_f32(0.3, True)), N.NMS_MODE_CPU_NMS, 100, det, ndet, keep, cnt, ks,
+                    workspace=ops.detect_post_workspace(R, Cc))
+    nd = int(ndet.item())
+    want_flat = np.vstack([np.hstack([d, np.full((d.shape[0], 1), j, F)]) for j, d in enumerate(want) if d.shape[0]])
+    assert nd == want_flat.shape[0]
+    assert np.array_equal(det.cpu().numpy()[:nd], want_flat)

@@ -51,14 +51,15 @@ SIGNATURES = {
     "frcnn_max_pool": (ci, [vp, vp, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp]),
     "frcnn_spatial_mean": (ci, [vp, vp, ci, ci, ci, vp]),
     "frcnn_preprocess": (ci, [vp, ci, ci, C.POINTER(C.c_double), C.c_double, C.c_double, vp, ci, ci, vp]),
-    "frcnn_rpn_decode": (ci, [vp, ci, ci, vp, ci, ci, ci, ci, cf, cf, vp, vp, vp]),
+    "frcnn_rpn_decode": (ci, [vp, ci, ci, vp, ci, ci, ci, ci, ci, cf, cf, vp, vp, vp]),
     "frcnn_sort_workspace_bytes": (sz, [ci]),
-    "frcnn_sort_desc": (ci, [vp, ci, vp, vp, vp, sz, vp]),
-    "frcnn_proposals": (ci, [vp, vp, vp, ci, ci, ci, cf, cu, vp, vp, vp, vp, vp]),
-    "frcnn_crop_pool": (ci, [vp, ci, ci, ci, vp, ci, ci, ci, vp, vp]),
+    "frcnn_sort_desc": (ci, [vp, ci, ci, vp, vp, vp, sz, vp]),
+    "frcnn_proposals": (ci, [vp, vp, vp, ci, ci, ci, ci, cf, cu, vp, vp, vp, vp, vp]),
+    "frcnn_crop_pool": (ci, [vp, ci, ci, ci, ci, vp, ci, ci, ci, vp, vp]),
     "frcnn_cls_finish": (ci, [vp, ci, ci, ci, fp, fp, vp, vp, vp, vp]),
-    "frcnn_bbox_decode": (ci, [vp, vp, ci, ci, cf, ci, ci, vp, vp]),
-    "frcnn_detect_post": (ci, [vp, vp, vp, ci, ci, cf, cf, cu, ci, ci, vp, vp, vp, vp, vp, vp]),
+    "frcnn_bbox_decode": (ci, [vp, vp, ci, ci, ci, vp, vp, vp]),
+    "frcnn_detect_post_workspace_bytes": (sz, [ci, ci, ci]),
+    "frcnn_detect_post": (ci, [vp, vp, vp, ci, ci, ci, cf, cf, cu, ci, ci, vp, vp, ci, vp, vp, vp, vp, sz, vp]),
 }
 
 _lib = None

@@ -11,7 +11,7 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
-SOURCES = ["api.cu", "conv_gemm.cu", "simt_ops.cu", "nms.cu"]
+SOURCES = ["api.cu", "conv_gemm.cu", "simt_ops.cu", "nms.cu", "sort.cu"]
 HEADERS = ["common.cuh", os.path.join("..", "..", "include", "frcnn_b200.h")]
 LIB = os.path.join(PKG, "libfrcnn_b200.so")
 NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
@@ -49,7 +49,7 @@ def build(force=False, verbose=False, watchdog=False):
             raise RuntimeError("nvcc failed for %s:\n%s" % (src, log))
         return log
 
-    with ThreadPoolExecutor(max_workers=4) as ex:
+    with ThreadPoolExecutor(max_workers=5) as ex:
         logs = list(ex.map(cc, jobs))
     if verbose:
         for l in logs:

@@ -14,7 +14,6 @@
 // variants (flags), so survivor indices are bit-exact.
 #include "common.cuh"
 #include "../../include/frcnn_b200.h"
-#include <cub/device/device_radix_sort.cuh>
 
 namespace frcnn {
 
@@ -179,13 +178,17 @@ __device__ void block_greedy_nms(CandFn cand, int m, float thr, unsigned flags, 
 constexpr int PROPOSAL_CAP = 1024;   // kept set held in shared memory (post_nms_top_n: 300 / 1000 / 'top' handled separately)
 
 __global__ void __launch_bounds__(NMS_THREADS, 1)
-proposals_kernel(const float4* __restrict__ props, const float* __restrict__ scores, const int* __restrict__ order, int m,
+proposals_kernel(const float4* __restrict__ props, const float* __restrict__ scores, const int* __restrict__ order, int n_seg, int m,
                  int max_out, float thr, unsigned flags, float* __restrict__ rois, float* __restrict__ roi_scores,
                  int* __restrict__ keep, int* __restrict__ num) {
   __shared__ GreedyShared sh;
   __shared__ float4 kept[PROPOSAL_CAP];
   __shared__ float kept_area[PROPOSAL_CAP];
   __shared__ int kept_pos[PROPOSAL_CAP];
+  // one CTA per image of the batch: segment blockIdx.x of the per-image arrays (order holds segment-local indices)
+  const int img = blockIdx.x;
+  props += (size_t)img * n_seg; scores += (size_t)img * n_seg; order += (size_t)img * n_seg;
+  rois += (size_t)img * max_out * 5; roi_scores += (size_t)img * max_out; keep += (size_t)img * max_out; num += img;
   block_greedy_nms([&](int i) { return __ldg(props + __ldg(order + i)); }, m, thr, flags, max_out, kept, kept_area, kept_pos, sh);
   const int nk = sh.nkept;
   for (int i = threadIdx.x; i < max_out; i += blockDim.x) {
@@ -193,7 +196,7 @@ proposals_kernel(const float4* __restrict__ props, const float* __restrict__ sco
     if (i < nk) {
       const int src = __ldg(order + kept_pos[i]);
       const float4 b = __ldg(props + src);   // un-normalised original box
-      r[0] = 0.f; r[1] = b.x; r[2] = b.y; r[3] = b.z; r[4] = b.w;
+      r[0] = (float)img; r[1] = b.x; r[2] = b.y; r[3] = b.z; r[4] = b.w;
       roi_scores[i] = __ldg(scores + src);
       keep[i] = src;
     } else {
@@ -207,8 +210,11 @@ proposals_kernel(const float4* __restrict__ props, const float* __restrict__ sco
 
 // 'top' mode (no NMS) with more outputs than the shared-memory kept set: plain gather of the first max_out
 __global__ void gather_top_kernel(const float4* __restrict__ props, const float* __restrict__ scores, const int* __restrict__ order,
-                                  int m, int max_out, float* __restrict__ rois, float* __restrict__ roi_scores,
+                                  int n_seg, int m, int max_out, float* __restrict__ rois, float* __restrict__ roi_scores,
                                   int* __restrict__ keep, int* __restrict__ num) {
+  const int img = blockIdx.y;
+  props += (size_t)img * n_seg; scores += (size_t)img * n_seg; order += (size_t)img * n_seg;
+  rois += (size_t)img * max_out * 5; roi_scores += (size_t)img * max_out; keep += (size_t)img * max_out; num += img;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i == 0) *num = min(m, max_out);
   if (i >= max_out) return;
@@ -216,7 +222,7 @@ __global__ void gather_top_kernel(const float4* __restrict__ props, const float*
   if (i < m) {
     const int src = __ldg(order + i);
     const float4 b = __ldg(props + src);
-    r[0] = 0.f; r[1] = b.x; r[2] = b.y; r[3] = b.z; r[4] = b.w;
+    r[0] = (float)img; r[1] = b.x; r[2] = b.y; r[3] = b.z; r[4] = b.w;
     roi_scores[i] = __ldg(scores + src);
     keep[i] = src;
   } else {
@@ -237,45 +243,62 @@ nms_sorted_kernel(const float* __restrict__ boxes, int stride, int m, float thr,
 }
 
 // ---- final per-class NMS + cap -----------------------------------------------------------------------------
-constexpr int DET_CAP = 1024;  // max RoIs per image handled by the per-class kernel (cfg 5 uses 1000)
+constexpr int DET_CAP = 1024;       // RoIs per image with the candidate list AND the kept set in shared memory (300 / 1000 proposals)
+constexpr int DET_CAP_BIG = 8192;   // TEST.MODE 'top' (RPN_TOP_N = 5000, lib/model/config.py:208): candidates in shared, kept set in global memory
 
-// one CTA per foreground class
+// one CTA per (foreground class, image).  CAP = power of two >= r.  Dynamic shared memory: skey[CAP] | sidx[CAP] and, when
+// !GLOBAL_KEPT, kept[CAP] (float4) | kept_area[CAP] | kept_pos[CAP]; with GLOBAL_KEPT those three live in `gws`
+// ([batch][C][r] slices, see frcnn_detect_post_workspace_bytes).
+template <int CAP, bool GLOBAL_KEPT>
 __global__ void __launch_bounds__(NMS_THREADS, 1)
 class_nms_kernel(const float* __restrict__ probs, const float4* __restrict__ pred, const int* __restrict__ num_rois, int r, int C,
                  float score_thresh, float nms_thresh, unsigned flags, int* __restrict__ keep, int* __restrict__ keep_cnt,
-                 float* __restrict__ keep_score) {
+                 float* __restrict__ keep_score, uint8_t* __restrict__ gws) {
   __shared__ GreedyShared sh;
-  __shared__ float4 kept[DET_CAP];
-  __shared__ float kept_area[DET_CAP];
-  __shared__ int kept_pos[DET_CAP];
-  __shared__ float skey[DET_CAP];
-  __shared__ int sidx[DET_CAP];
   __shared__ int s_m;
-  const int cls = blockIdx.x + 1;
+  extern __shared__ __align__(16) uint8_t cls_dyn[];
+  float4* kept; float* kept_area; int* kept_pos; float* skey; int* sidx;
+  const int cls = blockIdx.x + 1, img = blockIdx.y;
+  if (GLOBAL_KEPT) {
+    skey = reinterpret_cast<float*>(cls_dyn); sidx = reinterpret_cast<int*>(skey + CAP);
+    const size_t rr = (size_t)((r + 3) & ~3);          // slices stay 16-byte aligned
+    uint8_t* slice = gws + ((size_t)img * C + cls) * rr * 24;
+    kept = reinterpret_cast<float4*>(slice); kept_area = reinterpret_cast<float*>(slice + rr * 16);
+    kept_pos = reinterpret_cast<int*>(slice + rr * 20);
+  } else {
+    kept = reinterpret_cast<float4*>(cls_dyn); kept_area = reinterpret_cast<float*>(kept + CAP);
+    kept_pos = reinterpret_cast<int*>(kept_area + CAP); skey = reinterpret_cast<float*>(kept_pos + CAP); sidx = reinterpret_cast<int*>(skey + CAP);
+  }
+  probs += (size_t)img * r * C; pred += (size_t)img * r * C;
+  keep += (size_t)img * C * r; keep_score += (size_t)img * C * r; keep_cnt += (size_t)img * C;
   const int tid = threadIdx.x;
-  const int nr = min(*num_rois, r);
+  const int nr = min(__ldg(num_rois + img), r);
   // candidates: score > thresh (test.py:163); sort key (score desc, index asc); invalid -> -inf at the tail
   if (tid == 0) s_m = 0;
   __syncthreads();
-  {
+  int mine = 0;
+  for (int e = tid; e < CAP; e += NMS_THREADS) {
     float key = __int_as_float(0xff800000);
-    if (tid < nr) {
-      const float s = __ldg(probs + (size_t)tid * C + cls);
-      if (s > score_thresh) { key = s; atomicAdd(&s_m, 1); }
+    if (e < nr) {
+      const float s = __ldg(probs + (size_t)e * C + cls);
+      if (s > score_thresh) { key = s; ++mine; }
     }
-    skey[tid] = key; sidx[tid] = tid;
+    skey[e] = key; sidx[e] = e;
   }
+  if (mine) atomicAdd(&s_m, mine);
   __syncthreads();
-  // bitonic sort of 1024 (key desc, idx asc)
-  for (int k = 2; k <= DET_CAP; k <<= 1) {
+  // bitonic sort of CAP (key desc, idx asc)
+  for (int k = 2; k <= CAP; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
-      const int ixj = tid ^ j;
-      if (ixj > tid) {
-        const float a = skey[tid], b = skey[ixj];
-        const int ia = sidx[tid], ib = sidx[ixj];
-        const bool a_first = (a > b) || (a == b && ia < ib);   // a precedes b in the final order
-        const bool up = (tid & k) == 0;
-        if (up ? !a_first : a_first) { skey[tid] = b; skey[ixj] = a; sidx[tid] = ib; sidx[ixj] = ia; }
+      for (int e = tid; e < CAP; e += NMS_THREADS) {
+        const int ixj = e ^ j;
+        if (ixj > e) {
+          const float a = skey[e], b = skey[ixj];
+          const int ia = sidx[e], ib = sidx[ixj];
+          const bool a_first = (a > b) || (a == b && ia < ib);   // a precedes b in the final order
+          const bool up = (e & k) == 0;
+          if (up ? !a_first : a_first) { skey[e] = b; skey[ixj] = a; sidx[e] = ib; sidx[ixj] = ia; }
+        }
       }
       __syncthreads();
     }
@@ -284,7 +307,7 @@ class_nms_kernel(const float* __restrict__ probs, const float4* __restrict__ pre
   block_greedy_nms([&](int i) { return __ldg(pred + (size_t)sidx[i] * C + cls); }, m, nms_thresh, flags, m, kept, kept_area, kept_pos, sh);
   const int nk = sh.nkept;
   for (int i = tid; i < r; i += blockDim.x) {
-    if (i < nk) { keep[(size_t)cls * r + i] = sidx[kept_pos[i]]; keep_score[(size_t)cls * r + i] = skey[kept_pos[i]]; }
+    if (i < nk) { const int pos = kept_pos[i]; keep[(size_t)cls * r + i] = sidx[pos]; keep_score[(size_t)cls * r + i] = skey[pos]; }
     else { keep[(size_t)cls * r + i] = -1; keep_score[(size_t)cls * r + i] = 0.f; }
   }
   if (tid == 0) keep_cnt[cls] = nk;
@@ -309,10 +332,14 @@ __device__ __forceinline__ int count_ge(const float* __restrict__ sorted_desc, i
 
 __global__ void __launch_bounds__(NMS_THREADS, 1)
 cap_emit_kernel(const float4* __restrict__ pred, int r, int C, int max_per_image, int max_det, int* __restrict__ keep,
-                int* __restrict__ keep_cnt, const float* __restrict__ keep_score, float* __restrict__ det, int* __restrict__ ndet) {
+                int* __restrict__ keep_cnt, const float* __restrict__ keep_score, float* __restrict__ det, int* __restrict__ ndet,
+                int det_stride, int ndet_stride) {
   __shared__ int s_warp[NMS_THREADS / 32];
   __shared__ int s_total;
   __shared__ int s_off[1025];
+  const int img = blockIdx.x;                       // one CTA per image of the batch
+  pred += (size_t)img * r * C; keep += (size_t)img * C * r; keep_cnt += (size_t)img * C; keep_score += (size_t)img * C * r;
+  det += (size_t)img * det_stride; ndet += (size_t)img * ndet_stride;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool is_cls = tid >= 1 && tid < C;
   const int my_cnt = is_cls ? keep_cnt[tid] : 0;
@@ -350,7 +377,7 @@ cap_emit_kernel(const float4* __restrict__ pred, int r, int C, int max_per_image
   int before = 0;
   for (int w = 0; w < warp; ++w) before += s_warp[w];
   if (tid <= C) s_off[tid] = before + incl - v;
-  if (tid == NMS_THREADS - 1) { const int all = before + incl; *ndet = all < max_det ? all : max_det; }
+  if (tid == NMS_THREADS - 1) *ndet = before + incl;   // the TRUE count: the host rejects a record set that did not fit (> max_det)
   __syncthreads();
   for (int i = tid; i < (C - 1) * r; i += blockDim.x) {
     const int c = 1 + i / r, j = i % r;
@@ -367,50 +394,23 @@ cap_emit_kernel(const float4* __restrict__ pred, int r, int C, int max_per_image
   }
 }
 
-__global__ void iota_kernel(int* p, int n) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) p[i] = i;
-}
-
 }  // namespace frcnn
 
 using namespace frcnn;
 
-extern "C" size_t frcnn_sort_workspace_bytes(int n) {
-  size_t temp = 0;
-  cub::DeviceRadixSort::SortPairsDescending(nullptr, temp, (const float*)nullptr, (float*)nullptr, (const int*)nullptr, (int*)nullptr, n);
-  return ((temp + 255) / 256) * 256 + (size_t)n * sizeof(int) + 256;
-}
-
-// NOTE: the key sort itself is CUB's radix sort (CUDA toolkit header library) -- the one library kernel on the
-// path; stable, so equal scores keep ascending index order (= the oracle's tie rule).
-extern "C" int frcnn_sort_desc(const float* keys, int n, int* order, float* sorted_keys, void* workspace, size_t workspace_bytes, void* stream) {
-  FRCNN_REQUIRE(keys && order && sorted_keys && workspace && n > 0, "sort_desc: bad argument");
-  FRCNN_REQUIRE(workspace_bytes >= frcnn_sort_workspace_bytes(n), "sort_desc: workspace too small");
-  cudaStream_t st = (cudaStream_t)stream;
-  int* iota = reinterpret_cast<int*>(workspace);
-  const size_t iota_bytes = (((size_t)n * sizeof(int)) + 255) / 256 * 256;
-  void* temp = reinterpret_cast<uint8_t*>(workspace) + iota_bytes;
-  size_t temp_bytes = workspace_bytes - iota_bytes;
-  iota_kernel<<<cdiv(n, 256), 256, 0, st>>>(iota, n);
-  FRCNN_LAUNCH_CHECK();
-  FRCNN_CUDA(cub::DeviceRadixSort::SortPairsDescending(temp, temp_bytes, keys, sorted_keys, (const int*)iota, order, n, 0, 32, st));
-  return OK;
-}
-
-extern "C" int frcnn_proposals(const float* props, const float* scores, const int* order, int n, int pre_nms_top_n,
+extern "C" int frcnn_proposals(const float* props, const float* scores, const int* order, int n, int batch, int pre_nms_top_n,
                                int post_nms_top_n, float thresh, unsigned flags, float* rois, float* roi_scores, int* keep,
                                int* num, void* stream) {
-  FRCNN_REQUIRE(props && scores && order && rois && roi_scores && keep && num && n > 0 && post_nms_top_n > 0, "proposals: bad argument");
+  FRCNN_REQUIRE(props && scores && order && rois && roi_scores && keep && num && n > 0 && batch > 0 && post_nms_top_n > 0, "proposals: bad argument");
   const int m = (pre_nms_top_n > 0 && pre_nms_top_n < n) ? pre_nms_top_n : n;
   cudaStream_t st = (cudaStream_t)stream;
   if (thresh < 0.f) {
-    gather_top_kernel<<<cdiv(post_nms_top_n, 256), 256, 0, st>>>(reinterpret_cast<const float4*>(props), scores, order, m,
-                                                                 post_nms_top_n, rois, roi_scores, keep, num);
+    gather_top_kernel<<<dim3((unsigned)cdiv(post_nms_top_n, 256), (unsigned)batch), 256, 0, st>>>(
+        reinterpret_cast<const float4*>(props), scores, order, n, m, post_nms_top_n, rois, roi_scores, keep, num);
   } else {
     if (post_nms_top_n > PROPOSAL_CAP) { set_error("proposals: post_nms_top_n %d > capacity %d", post_nms_top_n, PROPOSAL_CAP); return ERR_CAPACITY; }
-    proposals_kernel<<<1, NMS_THREADS, 0, st>>>(reinterpret_cast<const float4*>(props), scores, order, m, post_nms_top_n, thresh,
-                                                flags, rois, roi_scores, keep, num);
+    proposals_kernel<<<(unsigned)batch, NMS_THREADS, 0, st>>>(reinterpret_cast<const float4*>(props), scores, order, n, m, post_nms_top_n,
+                                                             thresh, flags, rois, roi_scores, keep, num);
   }
   FRCNN_LAUNCH_CHECK();
   return OK;
@@ -465,17 +465,40 @@ extern "C" int frcnn_nms_host(int* keep_out, int* num_out, const float* boxes_ho
   return OK;
 }
 
-extern "C" int frcnn_detect_post(const float* cls_prob, const float* pred_boxes, const int* num_rois, int r, int num_classes,
+extern "C" size_t frcnn_detect_post_workspace_bytes(int r, int num_classes, int batch) {
+  if (r <= DET_CAP) return 256;
+  return (size_t)batch * num_classes * (size_t)((r + 3) & ~3) * 24 + 256;
+}
+
+extern "C" int frcnn_detect_post(const float* cls_prob, const float* pred_boxes, const int* num_rois, int r, int batch, int num_classes,
                                  float score_thresh, float nms_thresh, unsigned flags, int max_per_image, int max_det,
-                                 float* det, int* ndet, int* keep, int* keep_cnt, float* keep_score, void* stream) {
+                                 float* det, int* ndet, int record_stride, int* keep, int* keep_cnt, float* keep_score, void* workspace,
+                                 size_t workspace_bytes, void* stream) {
   FRCNN_REQUIRE(cls_prob && pred_boxes && num_rois && det && ndet && keep && keep_cnt && keep_score, "detect_post: null pointer");
-  FRCNN_REQUIRE(r > 0 && r <= DET_CAP && num_classes >= 2 && num_classes <= 1024, "detect_post: r<=%d, 2<=C<=1024 required", DET_CAP);
+  FRCNN_REQUIRE(r > 0 && batch > 0 && num_classes >= 2 && num_classes <= 1024, "detect_post: r>0, batch>0, 2<=C<=1024 required");
+  if (r > DET_CAP_BIG) { set_error("detect_post: %d RoIs per image > capacity %d", r, DET_CAP_BIG); return ERR_CAPACITY; }
   cudaStream_t st = (cudaStream_t)stream;
-  class_nms_kernel<<<num_classes - 1, NMS_THREADS, 0, st>>>(cls_prob, reinterpret_cast<const float4*>(pred_boxes), num_rois, r,
-                                                           num_classes, score_thresh, nms_thresh, flags, keep, keep_cnt, keep_score);
+  const dim3 grid((unsigned)(num_classes - 1), (unsigned)batch);
+  if (r <= DET_CAP) {
+    class_nms_kernel<DET_CAP, false><<<grid, NMS_THREADS, DET_CAP * 32, st>>>(cls_prob, reinterpret_cast<const float4*>(pred_boxes), num_rois, r,
+                                                                              num_classes, score_thresh, nms_thresh, flags, keep, keep_cnt,
+                                                                              keep_score, nullptr);
+  } else {
+    FRCNN_REQUIRE(workspace && workspace_bytes >= frcnn_detect_post_workspace_bytes(r, num_classes, batch), "detect_post: workspace too small");
+    static bool attr_done = false;
+    if (!attr_done) {
+      FRCNN_CUDA(cudaFuncSetAttribute(class_nms_kernel<DET_CAP_BIG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DET_CAP_BIG * 8));
+      attr_done = true;
+    }
+    class_nms_kernel<DET_CAP_BIG, true><<<grid, NMS_THREADS, DET_CAP_BIG * 8, st>>>(
+        cls_prob, reinterpret_cast<const float4*>(pred_boxes), num_rois, r, num_classes, score_thresh, nms_thresh, flags, keep, keep_cnt,
+        keep_score, reinterpret_cast<uint8_t*>(workspace));
+  }
   FRCNN_LAUNCH_CHECK();
-  cap_emit_kernel<<<1, NMS_THREADS, 0, st>>>(reinterpret_cast<const float4*>(pred_boxes), r, num_classes, max_per_image, max_det,
-                                            keep, keep_cnt, keep_score, det, ndet);
+  FRCNN_REQUIRE(record_stride == 0 || record_stride >= max_det * 6, "detect_post: record_stride %d < max_det*6", record_stride);
+  cap_emit_kernel<<<(unsigned)batch, NMS_THREADS, 0, st>>>(reinterpret_cast<const float4*>(pred_boxes), r, num_classes, max_per_image, max_det,
+                                                          keep, keep_cnt, keep_score, det, ndet,
+                                                          record_stride ? record_stride : max_det * 6, record_stride ? record_stride : 1);
   FRCNN_LAUNCH_CHECK();
   return OK;
 }

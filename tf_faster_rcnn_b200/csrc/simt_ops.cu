@@ -228,10 +228,13 @@ __device__ __forceinline__ float4 sample4(const float* __restrict__ feat, int fw
 constexpr int CROP_MAX_POOLED = 16;
 
 __global__ void __launch_bounds__(256)
-crop_pool_kernel(const float* __restrict__ feat, int fh, int fw, int c, const float* __restrict__ rois, int r, int pooled,
+crop_pool_kernel(const float* __restrict__ feat, int batch, int fh, int fw, int c, const float* __restrict__ rois, int r, int pooled,
                  int pre_pool, float* __restrict__ out) {
   __shared__ CropSample smp[CROP_MAX_POOLED * 4];           // [px][dy*2+dx] (one entry per px when !pre_pool)
   const int ri = blockIdx.x / pooled, py = blockIdx.x % pooled;
+  // crop_and_resize's box_ind = rois[:, 0] (network.py:143): which image of the batch the box is cut from
+  const int bi = min(max((int)__ldg(rois + (size_t)ri * 5), 0), batch - 1);
+  feat += (size_t)bi * fh * fw * c;
   const int nsub = pre_pool ? 4 : 1;
   if (threadIdx.x < pooled * nsub) {
     const int px = threadIdx.x / nsub, sub = threadIdx.x % nsub;
@@ -277,14 +280,15 @@ crop_pool_kernel(const float* __restrict__ feat, int fh, int fw, int c, const fl
 }
 
 // ---- RPN decode ---------------------------------------------------------------------------------------------
-__global__ void rpn_decode_kernel(const float* __restrict__ rpn, int ld, int delta_col, const float* __restrict__ base, int A, int fh,
-                                  int fw, int feat_stride, float im_h, float im_w, float* __restrict__ scores,
+__global__ void rpn_decode_kernel(const float* __restrict__ rpn, int ld, int delta_col, const float* __restrict__ base, int A, int batch,
+                                  int fh, int fw, int feat_stride, float im_h, float im_w, float* __restrict__ scores,
                                   float* __restrict__ props) {
-  const int total = fh * fw * A;
+  const int total = batch * fh * fw * A;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
-  const int a = i % A, pos = i / A;
-  const int gx = pos % fw, gy = pos / fw;
+  const int a = i % A, pos = i / A;                    // pos runs over the images of the batch
+  const int pin = pos % (fh * fw);
+  const int gx = pin % fw, gy = pin / fw;
   const float* row = rpn + (size_t)pos * ld;
   const float bg = __ldg(row + a), fg = __ldg(row + A + a);
   const float m = fmaxf(bg, fg);
@@ -333,12 +337,17 @@ __global__ void cls_finish_kernel(const float* __restrict__ head, int ld, int r,
 }
 
 // im_detect tail: thread per (roi, class)
-__global__ void bbox_decode_kernel(const float* __restrict__ rois, const float* __restrict__ deltas, int r, int C,
-                                   float im_scale, float xmax, float ymax, float* __restrict__ pred) {
+// im_meta [batch][3] = (im_scale, orig_h, orig_w) of every image, read from device memory so that the launch can sit in a
+// CUDA graph (r01 passed them by value and had to launch this tail eagerly after the graph)
+__global__ void bbox_decode_kernel(const float* __restrict__ rois, const float* __restrict__ deltas, int r, int C, int batch,
+                                   const float* __restrict__ im_meta, float* __restrict__ pred) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= r * C) return;
   const int row = i / C;
   const float* roi = rois + (size_t)row * 5;
+  const int bi = min(max((int)__ldg(roi), 0), batch - 1);
+  const float im_scale = __ldg(im_meta + bi * 3);
+  const float ymax = __fsub_rn(__ldg(im_meta + bi * 3 + 1), 1.f), xmax = __fsub_rn(__ldg(im_meta + bi * 3 + 2), 1.f);
   const float x1 = __fdiv_rn(__ldg(roi + 1), im_scale), y1 = __fdiv_rn(__ldg(roi + 2), im_scale);
   const float x2 = __fdiv_rn(__ldg(roi + 3), im_scale), y2 = __fdiv_rn(__ldg(roi + 4), im_scale);
   const float w = __fadd_rn(__fsub_rn(x2, x1), 1.f), h = __fadd_rn(__fsub_rn(y2, y1), 1.f);
@@ -466,21 +475,21 @@ extern "C" int frcnn_spatial_mean(const float* in, float* out, int r, int hw, in
   return OK;
 }
 
-extern "C" int frcnn_crop_pool(const float* feat, int fh, int fw, int c, const float* rois, int r, int pooled, int pre_pool,
+extern "C" int frcnn_crop_pool(const float* feat, int batch, int fh, int fw, int c, const float* rois, int r, int pooled, int pre_pool,
                                float* out, void* stream) {
-  FRCNN_REQUIRE(feat && rois && out && c % 4 == 0 && pooled > 1 && pooled <= CROP_MAX_POOLED, "crop_pool: bad argument");
-  crop_pool_kernel<<<(unsigned)(r * pooled), 256, 0, (cudaStream_t)stream>>>(feat, fh, fw, c, rois, r, pooled, pre_pool, out);
+  FRCNN_REQUIRE(feat && rois && out && batch > 0 && c % 4 == 0 && pooled > 1 && pooled <= CROP_MAX_POOLED, "crop_pool: bad argument");
+  crop_pool_kernel<<<(unsigned)(r * pooled), 256, 0, (cudaStream_t)stream>>>(feat, batch, fh, fw, c, rois, r, pooled, pre_pool, out);
   FRCNN_LAUNCH_CHECK();
   return OK;
 }
 
-extern "C" int frcnn_rpn_decode(const float* rpn_out, int ld, int delta_col, const float* base_anchors, int num_anchors, int fh, int fw,
-                                int feat_stride, float im_h, float im_w, float* scores, float* props, void* stream) {
-  FRCNN_REQUIRE(rpn_out && base_anchors && scores && props, "rpn_decode: null pointer");
+extern "C" int frcnn_rpn_decode(const float* rpn_out, int ld, int delta_col, const float* base_anchors, int num_anchors, int batch, int fh,
+                                int fw, int feat_stride, float im_h, float im_w, float* scores, float* props, void* stream) {
+  FRCNN_REQUIRE(rpn_out && base_anchors && scores && props && batch > 0, "rpn_decode: bad argument");
   FRCNN_REQUIRE(delta_col >= 2 * num_anchors && ld >= delta_col + 4 * num_anchors && (ld % 4) == 0 && (delta_col % 4) == 0,
                 "rpn_decode: ld/delta_col alignment");
-  const int total = fh * fw * num_anchors;
-  rpn_decode_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(rpn_out, ld, delta_col, base_anchors, num_anchors, fh, fw,
+  const long total = (long)batch * fh * fw * num_anchors;
+  rpn_decode_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(rpn_out, ld, delta_col, base_anchors, num_anchors, batch, fh, fw,
                                                                             feat_stride, im_h, im_w, scores, props);
   FRCNN_LAUNCH_CHECK();
   return OK;
@@ -497,11 +506,11 @@ extern "C" int frcnn_cls_finish(const float* head_out, int ld, int r, int num_cl
   return OK;
 }
 
-extern "C" int frcnn_bbox_decode(const float* rois, const float* bbox_pred, int r, int num_classes, float im_scale, int orig_h,
-                                 int orig_w, float* pred_boxes, void* stream) {
-  FRCNN_REQUIRE(rois && bbox_pred && pred_boxes, "bbox_decode: null pointer");
-  bbox_decode_kernel<<<blocks_for((long)r * num_classes, 256), 256, 0, (cudaStream_t)stream>>>(
-      rois, bbox_pred, r, num_classes, im_scale, (float)(orig_w - 1), (float)(orig_h - 1), pred_boxes);
+extern "C" int frcnn_bbox_decode(const float* rois, const float* bbox_pred, int r, int num_classes, int batch, const float* im_meta_dev,
+                                 float* pred_boxes, void* stream) {
+  FRCNN_REQUIRE(rois && bbox_pred && pred_boxes && im_meta_dev && batch > 0, "bbox_decode: bad argument");
+  bbox_decode_kernel<<<blocks_for((long)r * num_classes, 256), 256, 0, (cudaStream_t)stream>>>(rois, bbox_pred, r, num_classes, batch,
+                                                                                             im_meta_dev, pred_boxes);
   FRCNN_LAUNCH_CHECK();
   return OK;
 }

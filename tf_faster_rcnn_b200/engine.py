@@ -9,6 +9,8 @@ Layer semantics follow lib/nets/network.py:233-262 (graph order), :323-378 (head
 backbones emit their layers through the Tape from lib/nets/{vgg16,resnet_v1,mobilenet_v1}.py's
 counterparts in tf_faster_rcnn_b200/lib/nets/.
 """
+import ctypes
+
 import numpy as np
 import torch
 
@@ -16,6 +18,7 @@ from . import _native as N
 from . import ops
 
 F = np.float32
+C_void = ctypes.c_void_p
 
 
 def bn_fold(gamma, beta, mean, var, eps):
@@ -151,16 +154,26 @@ class Tape:
         return out
 
 
-class ShapePlan:
-    """Everything needed to run one blob shape: static input/output buffers, the tape, its CUDA graph."""
+REC_HEADER = 8     # 4-byte words in front of every image's detection rows: word 0 = int32 detection count
 
-    def __init__(self, net, h, w, use_graph=True):
-        self.net, self.h, self.w = net, h, w
+
+class ShapePlan:
+    """Everything needed to run `batch` images of one blob shape: static input/output buffers, the tape, its CUDA graphs.
+
+    The reference graph is batch 1 (lib/nets/network.py:388); batch > 1 is the throughput mode: the
+    backbone sees M = batch * H * W output pixels per layer (the 38x50 ResNet maps fill the 148 SMs without split-K), the
+    per-RoI head sees batch * R RoIs, and the single-CTA proposal / NMS kernels run one CTA per image side by side.
+    One image (or batch) = ONE graph replay: the im_detect / test_net tail is part of the graph, its per-image scalars
+    (scale, original size) are read from `im_meta` on the device."""
+
+    def __init__(self, net, h, w, batch=1, use_graph=True):
+        self.net, self.h, self.w, self.batch = net, h, w, batch
         cfgd = net.options
         wts = net.weights
         t = Tape(wts)
         self.tape = t
-        self.image = t.new(1, h, w, 3)
+        B = batch
+        self.image = t.new(B, h, w, 3)
         self.im_info = np.zeros(3, F)
         A = net.num_anchors
         C = net.num_classes
@@ -184,14 +197,14 @@ class ShapePlan:
         rpn_out = t.conv(rpn, sc + "/rpn_heads", 1, "SAME", N.ACT_NONE, packed=wts.packed_custom(sc + "/rpn_heads", fused_rpn))
         self.rpn_out, self.rpn_dcol = rpn_out, dcol
         nanch = fh * fw * A
-        self.rpn_scores = t.new(nanch); self.rpn_props = t.new(nanch, 4)
+        self.nanch = nanch
+        self.rpn_scores = t.new(B * nanch); self.rpn_props = t.new(B * nanch, 4)
         base = wts.dev("base_anchors/%s" % (net.anchor_key,), lambda: net.base_anchors)
         im_hw = (float(h), float(w))
-        t.add("rpn_decode", lambda: ops.rpn_decode(rpn_out.view(fh * fw, ld), dcol, base, A, fh, fw, im_hw[0], im_hw[1],
-                                                   self.rpn_scores, self.rpn_props))
-        self.order = t.new(nanch, dtype=torch.int32); self.sorted_scores = t.new(nanch)
-        sort_ws = ops.sort_workspace(nanch); t.bufs.append(sort_ws)
-        t.add("sort_desc", lambda: ops.sort_desc(self.rpn_scores, self.order, self.sorted_scores, sort_ws))
+        t.add("rpn_decode", lambda: ops.rpn_decode(rpn_out.view(B * fh * fw, ld), dcol, base, A, fh, fw, im_hw[0], im_hw[1],
+                                                   self.rpn_scores, self.rpn_props, batch=B))
+        self.order = t.new(B * nanch, dtype=torch.int32); self.sorted_scores = t.new(B * nanch)
+        t.add("sort_desc", lambda: ops.sort_desc(self.rpn_scores, self.order, self.sorted_scores, None, batch=B))
         # ---- proposals (proposal_layer_tf | proposal_layer | proposal_top_layer) ---------------------------
         if cfgd["test_mode"] == "top":
             R, pre, thr, flags = cfgd["rpn_top_n"], 0, -1.0, 0
@@ -201,14 +214,14 @@ class ShapePlan:
             R, pre = cfgd["rpn_post_nms_top_n"], cfgd["rpn_pre_nms_top_n"]
             thr, flags = nms_threshold(cfgd["rpn_nms_thresh"], cfgd["use_gpu_nms"])
         self.R = R
-        self.rois = t.new(R, 5); self.roi_scores = t.new(R)
-        self.roi_keep = t.new(R, dtype=torch.int32); self.num_rois = t.new(1, dtype=torch.int32)
+        self.rois = t.new(B * R, 5); self.roi_scores = t.new(B * R)
+        self.roi_keep = t.new(B * R, dtype=torch.int32); self.num_rois = t.new(B, dtype=torch.int32)
         t.add("proposals", lambda: ops.proposals(self.rpn_props, self.rpn_scores, self.order, pre, R, thr, flags, self.rois,
-                                                 self.roi_scores, self.roi_keep, self.num_rois))
+                                                 self.roi_scores, self.roi_keep, self.num_rois, batch=B))
         # ---- RoI pooling (network.py:141-157 / resnet_v1.py:55-76) ---------------------------------------
         P = cfgd["pooling_size"]
         pre_pool = net.crop_pre_pool()
-        self.pool5 = t.new(R, P, P, cb)
+        self.pool5 = t.new(B * R, P, P, cb)
         t.add("crop_pool", lambda: ops.crop_pool(feat, self.rois, P, pre_pool, self.pool5))
         # ---- per-RoI head + fused cls_score|bbox_pred FC (network.py:361-378) ------------------------------
         fc7 = net._head_to_tail(t, self.pool5)
@@ -223,48 +236,137 @@ class ShapePlan:
             bf[:C] = wts[sc + "/cls_score/biases"]; bf[C:5 * C] = wts[sc + "/bbox_pred/biases"]
             return wf, None, bf
         self.head_out = t.fc(fc7, sc + "/cls_bbox", N.ACT_NONE, packed=wts.packed_custom(sc + "/cls_bbox", fused_cls))
-        self.cls_score = t.new(R, C); self.cls_prob = t.new(R, C); self.bbox_pred = t.new(R, 4 * C)
+        self.cls_score = t.new(B * R, C); self.cls_prob = t.new(B * R, C); self.bbox_pred = t.new(B * R, 4 * C)
         stds, means = cfgd["bbox_stds"], cfgd["bbox_means"]
         t.add("cls_finish", lambda: ops.cls_finish(self.head_out, C, stds, means, self.cls_score, self.cls_prob, self.bbox_pred))
         self.n_test_image_steps = len(t.steps)
-        # ---- im_detect / test_net tail on device (test.py:95-107,162-180) ---------------------------------
-        self.pred_boxes = t.new(R, 4 * C)
-        self.post = dict(im_scale=1.0, orig_h=h, orig_w=w)
-        self.max_det = 2 * cfgd["max_per_image"] + 56 if cfgd["max_per_image"] > 0 else R * (C - 1)
-        self.det = t.new(self.max_det, 6); self.ndet = t.new(1, dtype=torch.int32)
-        self.keep = t.new(C, R, dtype=torch.int32); self.keep_cnt = t.new(C, dtype=torch.int32)
-        self.keep_score = t.new(C, R)
+        # ---- im_detect tail on the device (test.py:95-107): per-image (scale, orig_h, orig_w) live in im_meta --------------
+        self.pred_boxes = t.new(B * R, 4 * C)
+        self.im_meta = t.new(B, 3)
+        self.im_meta_host = torch.empty((B, 3), dtype=torch.float32).pin_memory() if torch.cuda.is_available() else torch.empty((B, 3))
+        self.im_meta_host[:] = torch.tensor([1.0, float(h), float(w)])
+        self.im_meta.copy_(self.im_meta_host)
+        t.add("bbox_decode", lambda: ops.bbox_decode(self.rois, self.bbox_pred, C, self.im_meta, self.pred_boxes))
+        self.n_im_detect_steps = len(t.steps)
+        # ---- test_net tail (test.py:162-180): built on first use for the options in force (_ensure_post) ---------------------
+        self.keep = t.new(B, C, R, dtype=torch.int32); self.keep_cnt = t.new(B, C, dtype=torch.int32)
+        self.keep_score = t.new(B, C, R)
+        self.post_ws = ops.detect_post_workspace(R, C, B); t.bufs.append(self.post_ws)
+        self.post_key = None
+        self.recs = [None, None]       # two record buffers; `double_buffer` makes consecutive detect launches alternate
+        self.rec = self.det = self.ndet = None   # ... views of the buffer the LAST detect launch wrote
+        self.post_steps = [None, None]
+        self.double_buffer = False
+        self.slot = 0
+        self.max_det = 0
         self.graphs = {}
         self.use_graph = use_graph
 
-    # the post-processing steps depend on per-image scalars (scale, original size): they are enqueued
-    # directly after the graph instead of being baked into it.
-    def _post(self, im_scale, orig_h, orig_w, detect):
-        net = self.net
-        C = net.num_classes
-        ops.bbox_decode(self.rois, self.bbox_pred, C, im_scale, orig_h, orig_w, self.pred_boxes)
-        if detect:
-            o = net.options
-            thr, flags = nms_threshold(o["nms_thresh"], o["use_gpu_nms"])
-            ops.detect_post(self.cls_prob, self.pred_boxes, self.num_rois, C, o["score_thresh"], thr, flags, o["max_per_image"],
-                            self.det, self.ndet, self.keep, self.keep_cnt, self.keep_score)
+    def nbytes(self):
+        return sum(b.numel() * b.element_size() for b in self.tape.bufs)
 
-    def launch(self, im_scale=1.0, orig_h=None, orig_w=None, post=False, detect=False):
-        """Enqueue one image (input already in self.image) on the current stream."""
+    def release(self):
+        """Drop graphs, conv plans (TMA descriptors, split-K workspaces) and activation buffers (LRU eviction)."""
+        self.graphs.clear()
+        self.tape.steps = []
+        self.tape.conv_plans = []
+        self.tape.bufs = []
+        self.post_steps = [None, None]
+        self.recs = [None, None]
+        self.rec = self.det = self.ndet = None
+
+    def _ensure_post(self):
+        """(Re)build the detection-record buffers and the post step for the current score / NMS thresholds and cap."""
+        net = self.net
+        o = net.options
+        key = (float(o["score_thresh"]), float(o["nms_thresh"]), bool(o["use_gpu_nms"]), int(o["max_per_image"]))
+        if key == self.post_key:
+            return
+        C, R, B = net.num_classes, self.R, self.batch
+        mpi = key[3]
+        # records: max_per_image survivors + head-room for ties at the threshold score; no cap -> every (roi, class) pair.
+        # A record set that still does not fit is reported through ndet > max_det and raised on the host (never truncated).
+        self.max_det = 2 * mpi + 56 if mpi > 0 else R * (C - 1)
+        stride = REC_HEADER + self.max_det * 6
+        thr, flags = nms_threshold(key[1], key[2])
+
+        def make_post(rec):
+            def post():
+                N.check(N.lib().frcnn_detect_post(ops._p(self.cls_prob), ops._p(self.pred_boxes), ops._p(self.num_rois), R, B, C, key[0],
+                                                  thr, flags, mpi, self.max_det, C_void(rec.data_ptr() + 4 * REC_HEADER), ops._p(rec), stride,
+                                                  ops._p(self.keep), ops._p(self.keep_cnt), ops._p(self.keep_score), ops._p(self.post_ws),
+                                                  self.post_ws.numel(), ops._stream()), "detect_post")
+            return post
+        self.recs = [torch.zeros((B, stride), dtype=torch.float32, device="cuda") for _ in range(2)]
+        self.post_steps = [make_post(r) for r in self.recs]
+        self.post_key = key
+        self._select(0)
+        self.graphs.pop(("detect", 0), None); self.graphs.pop(("detect", 1), None)
+
+    def _select(self, slot):
+        self.slot = slot
+        self.rec = self.recs[slot]
+        self.det = [self.rec[b, REC_HEADER:].view(self.max_det, 6) for b in range(self.batch)]
+        self.ndet = self.rec.view(torch.int32)[:, 0]
+
+    def steps_for(self, mode):
+        """mode: 'test_image' (network outputs), 'im_detect' (+ decoded boxes), 'detect' (+ per-class NMS, cap, records)."""
+        if mode == "test_image":
+            return [fn for _, fn in self.tape.steps[:self.n_test_image_steps]]
+        fns = [fn for _, fn in self.tape.steps[:self.n_im_detect_steps]]
+        if mode == "detect":
+            self._ensure_post()
+            fns.append(self.post_steps[self.slot])
+        return fns
+
+    def set_meta(self, rows):
+        """rows: per image (im_scale, orig_h, orig_w); staged in pinned memory, copied on the launching stream."""
+        for b, (s, oh, ow) in enumerate(rows):
+            self.im_meta_host[b, 0] = float(F(s)); self.im_meta_host[b, 1] = float(oh); self.im_meta_host[b, 2] = float(ow)
+        self.im_meta.copy_(self.im_meta_host, non_blocking=True)
+
+    def launch(self, im_scale=1.0, orig_h=None, orig_w=None, post=False, detect=False, meta=None):
+        """Enqueue one batch (inputs already in self.image) on the current stream.  meta: per-image (scale, orig_h, orig_w)
+        rows; the scalar arguments describe every image of the batch when meta is None."""
+        mode = "detect" if detect else ("im_detect" if post else "test_image")
+        if mode != "test_image":
+            if meta is None:
+                meta = [(im_scale, orig_h if orig_h is not None else self.h, orig_w if orig_w is not None else self.w)] * self.batch
+            self.set_meta(meta)
+        gkey = mode
+        if mode == "detect":
+            self._ensure_post()
+            self._select(self.slot ^ 1 if self.double_buffer else 0)
+            gkey = ("detect", self.slot)
         if self.use_graph:
-            g = self.graphs.get("main")
+            g = self.graphs.get(gkey)
             if g is None:
-                self.tape.run()                       # warm-up: function attributes, lazy allocations
+                fns = self.steps_for(mode)
+                for fn in fns:                        # warm-up: function attributes, lazy allocations
+                    fn()
                 torch.cuda.current_stream().synchronize()
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
-                    self.tape.run()
-                self.graphs["main"] = g
+                    for fn in fns:
+                        fn()
+                self.graphs[gkey] = g
             g.replay()
         else:
-            self.tape.run()
-        if post or detect:
-            self._post(float(F(im_scale)), int(orig_h if orig_h is not None else self.h), int(orig_w if orig_w is not None else self.w), detect)
+            for fn in self.steps_for(mode):
+                fn()
+
+    def records(self):
+        """Host copy of the detection records of the batch after a 'detect' launch: list of [n,6] arrays (one D2H copy)."""
+        host = self.rec.cpu()
+        counts = host.view(torch.int32)[:, 0].numpy()
+        out = []
+        for b in range(self.batch):
+            n = int(counts[b])
+            if n > self.max_det:
+                raise RuntimeError("image %d of the batch produced %d detections but the record buffer holds %d "
+                                   "(score ties beyond the max_per_image head-room)" % (b, n, self.max_det))
+            out.append(host[b, REC_HEADER:REC_HEADER + n * 6].view(n, 6).numpy().copy())
+        return out
 
 
 def nms_threshold(thresh, use_gpu_nms):

@@ -22,6 +22,9 @@ from utils.blob import im_list_to_blob
 from utils.timer import Timer
 
 FUSED_POST = True
+# Images per device launch in test_net's single-process loop (consecutive images with equal blob shapes are grouped).  1 = the
+# reference's data flow; tools/test_net.py --batch N raises it (throughput mode).
+BATCH_SIZE = 1
 # Opt-in: build the blob on the device from the uint8 image (mean subtraction + the cv2.resize
 # INTER_LINEAR arithmetic restated in a kernel, <= 1e-4 from OpenCV) instead of on the host.  Off by default so that the
 # default data flow is the reference's (host OpenCV blob).
@@ -82,7 +85,7 @@ def im_detect(sess, net, im):
         blobs['im_info'] = np.array([blob.shape[1], blob.shape[2], im_scales[0]], dtype=np.float32)
         plan = net._run(blob, blobs['im_info'], post=True, detect=False, orig_hw=im.shape[:2])
     torch.cuda.current_stream().synchronize()
-    r = int(plan.num_rois.item())
+    r = int(plan.num_rois[0].item())
     scores = plan.cls_prob[:r].cpu().numpy()
     if cfg.TEST.BBOX_REG:
         pred_boxes = plan.pred_boxes[:r].cpu().numpy()
@@ -130,28 +133,67 @@ def detect_image(net, im, thresh=0., max_per_image=100):
     blobs, im_scales = _get_blobs(im)
     blob = blobs['data']
     im_info = np.array([blob.shape[1], blob.shape[2], im_scales[0]], dtype=np.float32)
-    net.options["score_thresh"], net.options["max_per_image"] = float(thresh), int(max_per_image)
-    net.options["nms_thresh"] = cfg.TEST.NMS
+    _set_post_options(net, thresh, max_per_image)
     det, _ = net.detect(blob, im_info, im.shape[:2])
     C = net.num_classes
     cls = det[:, 5].astype(np.int64)
     return [det[cls == j, :5] for j in range(C)]
 
 
-def _detect_records(net, im, thresh, max_per_image):
-    """Fused path for one image, results left on the device: (det [max_det,6] fp32, ndet [1] int32), stream-ordered."""
+def _set_post_options(net, thresh, max_per_image):
+    net.options["score_thresh"], net.options["max_per_image"] = float(thresh), int(max_per_image)
+    net.options["nms_thresh"] = cfg.TEST.NMS
+
+
+def _detect_record(net, im, thresh, max_per_image):
+    """Fused path for one image, result left on the device: the plan's record buffer of this launch
+    ([REC_HEADER + max_det*6] fp32, int32 count in word 0), stream-ordered.  Consecutive launches of a plan alternate between
+    two record buffers, so the record stays valid while the NEXT image runs (the sharded loop gathers it meanwhile)."""
     blobs, im_scales = _get_blobs(im)
     blob = blobs['data']
     im_info = np.array([blob.shape[1], blob.shape[2], im_scales[0]], dtype=np.float32)
-    net.options["score_thresh"], net.options["max_per_image"] = float(thresh), int(max_per_image)
-    net.options["nms_thresh"] = cfg.TEST.NMS
+    _set_post_options(net, thresh, max_per_image)
+    plan = net.plan_for(blob.shape[1], blob.shape[2])
+    plan.double_buffer = True
     plan = net._run(blob, im_info, post=True, detect=True, orig_hw=im.shape[:2])
-    return plan.det, plan.ndet
+    return plan.rec[0]
 
 
-def _test_net_sharded(imdb, detect_records, verbose=True):
+def detect_images(net, ims, thresh=0., max_per_image=100, batch_size=None):
+    """Several images through the fused device path, grouping CONSECUTIVE images whose blobs have the same shape into batches
+    of up to `batch_size` (default BATCH_SIZE).  -> per image a list over classes of fp32 [k,5].  Batch 1 is the reference's
+    data flow; larger batches are the throughput extension (same per-image arithmetic, M = batch * pixels per layer)."""
+    bs = int(batch_size or BATCH_SIZE)
+    _set_post_options(net, thresh, max_per_image)
+    C = net.num_classes
+    prepared = []
+    for im in ims:
+        blobs, im_scales = _get_blobs(im)
+        prepared.append((blobs['data'], float(im_scales[0]), im.shape[:2]))
+    out = [None] * len(ims)
+    i = 0
+    while i < len(prepared):
+        j = i + 1
+        while j < len(prepared) and j - i < bs and prepared[j][0].shape == prepared[i][0].shape:
+            j += 1
+        group = prepared[i:j]
+        if len(group) == 1:
+            b0, s0, hw0 = group[0]
+            dets = [net.detect(b0, np.array([b0.shape[1], b0.shape[2], s0], np.float32), hw0)[0]]
+        else:
+            dets, _ = net.detect_batch(np.concatenate([g[0] for g in group], axis=0), [g[1] for g in group], [g[2] for g in group])
+        for k, det in enumerate(dets):
+            cls = det[:, 5].astype(np.int64)
+            out[i + k] = [det[cls == c, :5] for c in range(C)]
+        i = j
+    return out
+
+
+def _test_net_sharded(imdb, detect_record, verbose=True):
     """Lock-step loop over ceil(N / W) steps; every rank returns the complete all_boxes[cls][image].
-    detect_records(image index) -> (det [max_det,6] float tensor, ndet [1] int32 tensor) on the collective's device."""
+    detect_record(image index) -> record tensor [REC_HEADER + max_det*6] fp32 (int32 count in word 0) on the collective's
+    device, valid until two more records have been produced.  ONE all-gather per step, issued asynchronously: while it is in
+    flight the rank already runs its next image, and the previous step's gathered records are scattered on the host."""
     import torch.distributed as dist
     from tf_faster_rcnn_b200 import parallel
     rank, world = dist.get_rank(), dist.get_world_size()
@@ -161,23 +203,28 @@ def _test_net_sharded(imdb, detect_records, verbose=True):
     device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
     gather = idle = None
     timer = Timer()
-    for step in range(parallel.steps_for(num_images, world)):
+    nsteps = parallel.steps_for(num_images, world)
+    for step in range(nsteps):
         timer.tic()
-        rec = detect_records(mine[step]) if step < len(mine) else None
+        slot = step & 1
+        if gather is not None:
+            gather.before_overwrite(slot)              # the gather of step-2 has read the record buffer about to be reused
+        rec = detect_record(mine[step]) if step < len(mine) else None
         if gather is None:
-            # ranks without an image (N < W) learn the record capacity from the others: one extra tiny collective, once
-            cap = torch.tensor([rec[0].shape[0] if rec is not None else 0], dtype=torch.int64, device=device)
+            # ranks without an image (N < W) learn the record size from the others: one extra tiny collective, once
+            cap = torch.tensor([rec.numel() if rec is not None else 0], dtype=torch.int64, device=device)
             dist.all_reduce(cap, op=dist.ReduceOp.MAX)
-            idle = (torch.zeros(int(cap.item()), 6, dtype=torch.float32, device=device),
-                    torch.zeros(1, dtype=torch.int32, device=device))
-            gather = parallel.RecordGather(idle[0], idle[1], world)
-        det, ndet = rec if rec is not None else idle
-        det_list, n_list = gather.gather(det, ndet)
-        parallel.records_to_all_boxes(all_boxes, step, world, det_list, n_list, num_images)
+            idle = torch.zeros(int(cap.item()), dtype=torch.float32, device=device)
+            gather = parallel.RecordGather(idle, world)
+        gather.issue(slot, rec if rec is not None else idle)
+        if step > 0:
+            parallel.records_to_all_boxes(all_boxes, step - 1, world, gather.result(slot ^ 1), num_images)
         timer.toc()
         if verbose and rank == 0:
             print('im_detect: {:d}/{:d} {:.3f}s per step of {:d} images'.format(
                 min((step + 1) * world, num_images), num_images, timer.average_time, world))
+    if nsteps > 0:
+        parallel.records_to_all_boxes(all_boxes, nsteps - 1, world, gather.result((nsteps - 1) & 1), num_images)
     return all_boxes
 
 
@@ -190,7 +237,7 @@ def test_net(sess, net, imdb, weights_filename, max_per_image=100, thresh=0.):
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         assert FUSED_POST and cfg.TEST.BBOX_REG, "sharded test_net gathers the fused path's device records"
         all_boxes = _test_net_sharded(
-            imdb, lambda i: _detect_records(net, cv2.imread(imdb.image_path_at(i)), thresh, max_per_image))
+            imdb, lambda i: _detect_record(net, cv2.imread(imdb.image_path_at(i)), thresh, max_per_image))
         if dist.get_rank() == 0:
             with open(os.path.join(output_dir, 'detections.pkl'), 'wb') as f:
                 pickle.dump(all_boxes, f, pickle.HIGHEST_PROTOCOL)
@@ -200,23 +247,35 @@ def test_net(sess, net, imdb, weights_filename, max_per_image=100, thresh=0.):
         return all_boxes
     all_boxes = [[[] for _ in range(num_images)] for _ in range(imdb.num_classes)]
     _t = {'im_detect': Timer(), 'misc': Timer()}
-    for i in range(num_images):
-        im = cv2.imread(imdb.image_path_at(i))
-        if FUSED_POST and cfg.TEST.BBOX_REG:
+    if FUSED_POST and cfg.TEST.BBOX_REG and BATCH_SIZE > 1:
+        for i0 in range(0, num_images, BATCH_SIZE):
+            ims = [cv2.imread(imdb.image_path_at(i)) for i in range(i0, min(i0 + BATCH_SIZE, num_images))]
             _t['im_detect'].tic()
-            per_class = detect_image(net, im, thresh, max_per_image)
+            results = detect_images(net, ims, thresh, max_per_image)
             _t['im_detect'].toc()
-            _t['misc'].tic()
-        else:
-            _t['im_detect'].tic()
-            scores, boxes = im_detect(sess, net, im)
-            _t['im_detect'].toc()
-            _t['misc'].tic()
-            per_class = _detections_python_loop(scores, boxes, imdb.num_classes, thresh, max_per_image)
-        for j in range(1, imdb.num_classes):
-            all_boxes[j][i] = per_class[j]
-        _t['misc'].toc()
-        print('im_detect: {:d}/{:d} {:.3f}s {:.3f}s'.format(i + 1, num_images, _t['im_detect'].average_time, _t['misc'].average_time))
+            for k, per_class in enumerate(results):
+                for j in range(1, imdb.num_classes):
+                    all_boxes[j][i0 + k] = per_class[j]
+            print('im_detect: {:d}/{:d} {:.3f}s per batch of {:d}'.format(min(i0 + BATCH_SIZE, num_images), num_images,
+                                                                          _t['im_detect'].average_time, BATCH_SIZE))
+    else:
+        for i in range(num_images):
+            im = cv2.imread(imdb.image_path_at(i))
+            if FUSED_POST and cfg.TEST.BBOX_REG:
+                _t['im_detect'].tic()
+                per_class = detect_image(net, im, thresh, max_per_image)
+                _t['im_detect'].toc()
+                _t['misc'].tic()
+            else:
+                _t['im_detect'].tic()
+                scores, boxes = im_detect(sess, net, im)
+                _t['im_detect'].toc()
+                _t['misc'].tic()
+                per_class = _detections_python_loop(scores, boxes, imdb.num_classes, thresh, max_per_image)
+            for j in range(1, imdb.num_classes):
+                all_boxes[j][i] = per_class[j]
+            _t['misc'].toc()
+            print('im_detect: {:d}/{:d} {:.3f}s {:.3f}s'.format(i + 1, num_images, _t['im_detect'].average_time, _t['misc'].average_time))
     with open(os.path.join(output_dir, 'detections.pkl'), 'wb') as f:
         pickle.dump(all_boxes, f, pickle.HIGHEST_PROTOCOL)
     print('Evaluating detections')

@@ -4,6 +4,8 @@ _image_to_head / _head_to_tail (:380-384).  Instead of building a TF graph, crea
 the options; the first test_image for a blob shape builds a ShapePlan (device buffers, TMA-backed conv
 plans, CUDA graph) and later calls replay it.  `sess` arguments are accepted and ignored.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -56,7 +58,7 @@ class Network(object):
         """-> (cls_score, cls_prob, bbox_pred, rois) host fp32 arrays, rois in blob-scale pixels."""
         plan = self._run(image, im_info)
         torch.cuda.current_stream().synchronize()
-        r = int(plan.num_rois.item())
+        r = int(plan.num_rois[0].item())
         out = (plan.cls_score[:r].cpu().numpy(), plan.cls_prob[:r].cpu().numpy(), plan.bbox_pred[:r].cpu().numpy(),
                plan.rois[:r].cpu().numpy())
         return out
@@ -112,31 +114,54 @@ class Network(object):
         self.weights = engine.Weights(dict(tensors))
         self._plans = {}
 
-    def plan_for(self, h, w):
+    MAX_PLANS = int(os.environ.get("FRCNN_MAX_PLANS", "6"))
+
+    def plan_for(self, h, w, batch=1):
+        """ShapePlan of blob shape (h, w) x batch.  A plan owns every layer's activation buffer, the TMA descriptors and the CUDA
+        graphs of that shape (0.6-1.3 GB per image at 600x800..1000), so the cache is a small LRU: a dataset with hundreds of
+        distinct shapes recycles plans instead of growing without bound (evicted buffers return to the caching allocator)."""
         if self.weights is None:
             raise RuntimeError("no weights loaded: call load_weights() / Saver.restore() before test_image")
-        key = (int(h), int(w))
-        if key not in self._plans:
+        key = (int(h), int(w), int(batch))
+        plan = self._plans.pop(key, None)
+        if plan is None:
             dev = torch.cuda.current_device() if torch.cuda.is_available() else 0
             _native.check(_native.lib().frcnn_check_device(dev), "check_device")   # fails loudly: no CPU fallback exists
-            self._plans[key] = engine.ShapePlan(self, key[0], key[1], use_graph=self.use_cuda_graph)
-        return self._plans[key]
+            while len(self._plans) >= max(1, self.MAX_PLANS):
+                old_key = next(iter(self._plans))
+                old = self._plans.pop(old_key)
+                torch.cuda.current_stream().synchronize()   # nothing of the evicted plan is still in flight
+                old.release()
+            plan = engine.ShapePlan(self, key[0], key[1], key[2], use_graph=self.use_cuda_graph)
+        self._plans[key] = plan                             # most recently used last
+        return plan
 
-    def _run(self, image, im_info, post=False, detect=False, orig_hw=None):
-        assert image.shape[0] == 1 and image.shape[3] == 3, "Only single-image batch implemented"
-        plan = self.plan_for(image.shape[1], image.shape[2])
+    def _copy_in(self, plan, image):
         if isinstance(image, torch.Tensor):
             plan.image.copy_(image, non_blocking=True)
         else:
             plan.image.copy_(torch.from_numpy(np.ascontiguousarray(image, dtype=np.float32)), non_blocking=True)
+
+    def _run(self, image, im_info, post=False, detect=False, orig_hw=None):
+        assert image.shape[0] == 1 and image.shape[3] == 3, "test_image / im_detect take ONE image (use detect_batch for more)"
+        plan = self.plan_for(image.shape[1], image.shape[2])
+        self._copy_in(plan, image)
         oh, ow = orig_hw if orig_hw is not None else (None, None)
         plan.launch(float(im_info[2]), oh, ow, post=post, detect=detect)
         return plan
 
     def detect(self, image, im_info, orig_hw):
         """Fused device path for im_detect + test_net's per-class NMS + max_per_image cap.
-        Returns (det [n,6] = x1,y1,x2,y2,score,class; plan) after one stream sync."""
+        Returns (det [n,6] = x1,y1,x2,y2,score,class; plan) after one stream sync (one D2H copy of the record)."""
         plan = self._run(image, im_info, post=True, detect=True, orig_hw=orig_hw)
-        torch.cuda.current_stream().synchronize()
-        n = int(plan.ndet.item())
-        return plan.det[:n].cpu().numpy(), plan
+        return plan.records()[0], plan
+
+    def detect_batch(self, images, im_scales, orig_hws):
+        """Throughput path: `images` [B,H,W,3] blobs of ONE shape (numpy or a pinned torch tensor), per-image scale factors and
+        original (h, w).  -> (list of B det arrays [n,6], plan).  The reference is batch 1; this is SURVEY 8(f) rank 4."""
+        b = int(images.shape[0])
+        assert images.shape[3] == 3 and len(im_scales) == b and len(orig_hws) == b
+        plan = self.plan_for(images.shape[1], images.shape[2], b)
+        self._copy_in(plan, images)
+        plan.launch(post=True, detect=True, meta=[(float(im_scales[i]), int(orig_hws[i][0]), int(orig_hws[i][1])) for i in range(b)])
+        return plan.records(), plan

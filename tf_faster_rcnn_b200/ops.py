@@ -89,6 +89,7 @@ class ConvPlan:
         self._h = C.c_void_p()
         N.check(N.lib().frcnn_conv_plan_create(C.byref(self._h), C.byref(d)), "conv_plan_create")
         self._keep = (x, pc, out, residual)
+        self.flops = 2.0 * n * ho * wo * pc.cout * pc.kh * pc.kw * pc.cin
 
     def run(self):
         N.check(N.lib().frcnn_conv_plan_run(self._h, _stream()), "conv_plan_run")
@@ -152,9 +153,10 @@ def preprocess(img_u8_dev, means3, fx, fy, blob):
             "preprocess")
 
 
-def rpn_decode(rpn_out, delta_col, base_anchors, num_anchors, fh, fw, im_h, im_w, scores, props, feat_stride=16):
+def rpn_decode(rpn_out, delta_col, base_anchors, num_anchors, fh, fw, im_h, im_w, scores, props, feat_stride=16, batch=1):
+    """rpn_out: [batch*fh*fw, ld] rows of the fused RPN head."""
     ld = rpn_out.shape[-1]
-    N.check(N.lib().frcnn_rpn_decode(_p(_f32(rpn_out)), ld, delta_col, _p(base_anchors), num_anchors, fh, fw, feat_stride,
+    N.check(N.lib().frcnn_rpn_decode(_p(_f32(rpn_out)), ld, delta_col, _p(base_anchors), num_anchors, batch, fh, fw, feat_stride,
                                      float(im_h), float(im_w), _p(scores), _p(props), _stream()), "rpn_decode")
 
 
@@ -162,22 +164,24 @@ def sort_workspace(n):
     return torch.empty(int(N.lib().frcnn_sort_workspace_bytes(n)), dtype=torch.uint8, device="cuda")
 
 
-def sort_desc(keys, order, sorted_keys, workspace):
-    n = keys.numel()
-    N.check(N.lib().frcnn_sort_desc(_p(_f32(keys)), n, _p(order), _p(sorted_keys), _p(workspace), workspace.numel(), _stream()),
-            "sort_desc")
+def sort_desc(keys, order, sorted_keys, workspace=None, batch=1):
+    """`batch` segments of keys.numel() // batch keys each; order = segment-local indices."""
+    n = keys.numel() // batch
+    N.check(N.lib().frcnn_sort_desc(_p(_f32(keys)), n, batch, _p(order), _p(sorted_keys), _p(workspace),
+                                    0 if workspace is None else workspace.numel(), _stream()), "sort_desc")
 
 
-def proposals(props, scores, order, pre_nms_top_n, post_nms_top_n, thresh, flags, rois, roi_scores, keep, num):
-    n = scores.numel()
-    N.check(N.lib().frcnn_proposals(_p(props), _p(scores), _p(order), n, pre_nms_top_n, post_nms_top_n, float(thresh), flags,
+def proposals(props, scores, order, pre_nms_top_n, post_nms_top_n, thresh, flags, rois, roi_scores, keep, num, batch=1):
+    n = scores.numel() // batch
+    N.check(N.lib().frcnn_proposals(_p(props), _p(scores), _p(order), n, batch, pre_nms_top_n, post_nms_top_n, float(thresh), flags,
                                     _p(rois), _p(roi_scores), _p(keep), _p(num), _stream()), "proposals")
 
 
 def crop_pool(feat, rois, pooled, pre_pool, out):
-    _, fh, fw, c = feat.shape
+    """rois[:, 0] = index of the image (of feat's batch dimension) the box is cut from."""
+    b, fh, fw, c = feat.shape
     r = rois.shape[0]
-    N.check(N.lib().frcnn_crop_pool(_p(_f32(feat)), fh, fw, c, _p(_f32(rois)), r, pooled, int(pre_pool), _p(_f32(out)), _stream()),
+    N.check(N.lib().frcnn_crop_pool(_p(_f32(feat)), b, fh, fw, c, _p(_f32(rois)), r, pooled, int(pre_pool), _p(_f32(out)), _stream()),
             "crop_pool")
 
 
@@ -189,18 +193,32 @@ def cls_finish(head_out, num_classes, stds, means, cls_score, cls_prob, bbox_pre
                                      _stream()), "cls_finish")
 
 
-def bbox_decode(rois, bbox_pred, num_classes, im_scale, orig_h, orig_w, pred_boxes):
+def im_meta_tensor(rows):
+    """[(im_scale, orig_h, orig_w), ...] -> device fp32 [batch, 3] (the per-image scalars bbox_decode reads)."""
+    return torch.tensor([[float(np.float32(s)), float(h), float(w)] for s, h, w in rows], dtype=torch.float32).cuda()
+
+
+def bbox_decode(rois, bbox_pred, num_classes, im_meta, pred_boxes):
+    """im_meta: device fp32 [batch, 3] (im_scale, orig_h, orig_w); rois[:, 0] selects the row."""
     r = rois.shape[0]
-    N.check(N.lib().frcnn_bbox_decode(_p(_f32(rois)), _p(_f32(bbox_pred)), r, num_classes, float(np.float32(im_scale)), int(orig_h),
-                                      int(orig_w), _p(pred_boxes), _stream()), "bbox_decode")
+    N.check(N.lib().frcnn_bbox_decode(_p(_f32(rois)), _p(_f32(bbox_pred)), r, num_classes, im_meta.shape[0], _p(_f32(im_meta)),
+                                      _p(pred_boxes), _stream()), "bbox_decode")
+
+
+def detect_post_workspace(r, num_classes, batch=1):
+    return torch.empty(int(N.lib().frcnn_detect_post_workspace_bytes(r, num_classes, batch)), dtype=torch.uint8, device="cuda")
 
 
 def detect_post(cls_prob, pred_boxes, num_rois, num_classes, score_thresh, nms_thresh, flags, max_per_image, det, ndet, keep,
-                keep_cnt, keep_score):
-    r = cls_prob.shape[0]
-    N.check(N.lib().frcnn_detect_post(_p(cls_prob), _p(pred_boxes), _p(num_rois), r, num_classes, float(score_thresh),
-                                      float(nms_thresh), flags, max_per_image, det.shape[0], _p(det), _p(ndet), _p(keep),
-                                      _p(keep_cnt), _p(keep_score), _stream()), "detect_post")
+                keep_cnt, keep_score, workspace=None, batch=1):
+    """cls_prob [batch*r, C]; det [batch, max_det, 6] (or [max_det, 6] for batch 1); ndet int32 [batch] = TRUE counts
+    (a count above max_det means the records did not fit)."""
+    r = cls_prob.shape[0] // batch
+    max_det = det.shape[-2]
+    N.check(N.lib().frcnn_detect_post(_p(cls_prob), _p(pred_boxes), _p(num_rois), r, batch, num_classes, float(score_thresh),
+                                      float(nms_thresh), flags, max_per_image, max_det, _p(det), _p(ndet), 0, _p(keep),
+                                      _p(keep_cnt), _p(keep_score), _p(workspace), 0 if workspace is None else workspace.numel(),
+                                      _stream()), "detect_post")
 
 
 def nms_sorted_dev(boxes, thresh, flags, max_out, keep, num):

@@ -27,6 +27,8 @@ def parse_args():
     p.add_argument('--num_dets', dest='max_per_image', default=100, type=int)
     p.add_argument('--tag', dest='tag', default='', type=str)
     p.add_argument('--net', dest='net', default='res50', type=str, help='vgg16, res50, res101, res152, mobile')
+    p.add_argument('--batch', dest='batch', default=1, type=int,
+                   help='images per device launch: consecutive images with equal blob shapes are grouped (not in the reference)')
     p.add_argument('--set', dest='set_cfgs', default=None, nargs=argparse.REMAINDER)
     return p.parse_args()
 
@@ -56,4 +58,6 @@ if __name__ == '__main__':
     imdb = get_imdb(args.imdb_name)
     imdb.competition_mode(args.comp_mode)
     net = build_net(args.net, imdb.num_classes, args.model)
+    import model.test as model_test
+    model_test.BATCH_SIZE = max(1, args.batch)
     test_net(None, net, imdb, filename + '/' + tag, max_per_image=args.max_per_image)
