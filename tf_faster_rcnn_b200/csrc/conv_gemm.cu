@@ -76,6 +76,7 @@ struct ConvKernelParams {
   // runs the epilogue (r02 measured an in-kernel 'last CTA to arrive reduces' fix-up: 21 us instead of 13 us for a 38x50 1x1 layer).
   int kb_per_split;
   int m_tiles, n_tiles, total_units, n_full, splits;
+  int raster_n;       // 1: consecutive tile indices walk the N-blocks of one M-tile (activations streamed once), 0: M-tiles first
   float* ws;
   long long* trace;   // debug: clock64() stamps of CTA (0,0)'s pipeline hand-offs; normally NULL
   int num_kb_total;   // f16x3: 64-wide k-blocks of the whole K loop
@@ -118,8 +119,12 @@ __device__ __forceinline__ Unit decode_unit(const ConvKernelParams& p, int u, in
   int tile;
   if (u < p.n_full) { tile = u; t.z = 0; t.slot = -1; }
   else { const int v = u - p.n_full; t.slot = v / p.splits; t.z = v - t.slot * p.splits; tile = p.n_full + t.slot; }
-  const int mt = tile % p.m_tiles;
-  t.nblk = tile / p.m_tiles;
+  // raster order of the tile index (r02 finding 4, ncu on the batch-4 head: with all M-tiles of one N-block first, the 241 MB
+  // activation of block4's shortcut was streamed from DRAM once per N-block -- 16 x, 3.9 GB, DRAM 67 % busy): the operand
+  // with the larger footprint is walked ONCE, the other one stays L2 resident (decide_geometry sets raster_n).
+  int mt;
+  if (p.raster_n) { t.nblk = tile % p.n_tiles; mt = tile / p.n_tiles; }
+  else { mt = tile % p.m_tiles; t.nblk = tile / p.m_tiles; }
   const int tile_w = mt % p.tiles_w;
   const int tile_h = (mt / p.tiles_w) % p.tiles_h;
   const int tile_n = mt / (p.tiles_w * p.tiles_h);
@@ -816,7 +821,7 @@ tail_reduce_kernel(const ConvKernelParams p) {
   constexpr int GROUPS = BLOCK_M / RPB;
   const int slot = blockIdx.x / GROUPS, rgroup = blockIdx.x % GROUPS;
   const int tile = p.n_full + slot;
-  const int mt = tile % p.m_tiles, nblk = tile / p.m_tiles;
+  const int mt = p.raster_n ? tile / p.n_tiles : tile % p.m_tiles, nblk = p.raster_n ? tile % p.n_tiles : tile / p.m_tiles;
   const int tile_w = mt % p.tiles_w, tile_h = (mt / p.tiles_w) % p.tiles_h, tile_n = mt / (p.tiles_w * p.tiles_h);
   const int rows_img = p.th * p.tw;
   constexpr int C4 = BN / 4;
@@ -1010,6 +1015,7 @@ struct Geometry {
   int splits, kbs;
   long total_units;
   int grid;
+  int raster_n;
 };
 
 static int decide_geometry(const frcnn_conv_desc* d, int sms, Geometry* g) {
@@ -1072,6 +1078,11 @@ static int decide_geometry(const frcnn_conv_desc* d, int sms, Geometry* g) {
   g->total_units = (g->tiles - n_tail) + n_tail * splits;
   FRCNN_REQUIRE(g->total_units <= 0x7fffffffL, "too many work units");
   g->grid = (int)(g->total_units < sms ? g->total_units : sms);   // persistent: one CTA per SM walks the units
+  {
+    const char* e = getenv("FRCNN_CONV_RASTER");          // development override: m | n
+    const double a_bytes = (double)d->n * d->h * d->w * d->cin * 4.0, b_bytes = (double)d->cout * d->kh * d->kw * d->cin * 4.0;
+    g->raster_n = (e && (e[0] == 'm' || e[0] == 'n')) ? (e[0] == 'n') : (a_bytes > b_bytes && g->n_tiles > 1);
+  }
   return OK;
 }
 
@@ -1134,6 +1145,7 @@ extern "C" int frcnn_conv_plan_create(frcnn_conv_plan** out, const frcnn_conv_de
   k.m_tiles = (int)g.m_tiles; k.n_tiles = g.n_tiles;
   k.kb_per_split = g.kbs; k.splits = g.splits; k.n_full = (int)(g.tiles - g.n_tail);
   k.total_units = (int)g.total_units;
+  k.raster_n = g.raster_n;
   k.ws = nullptr; p->ws = nullptr; p->eff = nullptr; p->n_tail = (int)g.n_tail;
   {
     // NOTE: the vectors are snapshots of scale_dev / shift_dev taken now (they are weights: constant after load)
