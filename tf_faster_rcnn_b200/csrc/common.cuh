@@ -152,6 +152,37 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, ui
       "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
       ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
+// same, the shared-memory descriptor given as (low word, constant high word); `accumulate` run-time
+__device__ __forceinline__ void umma_f16_ts_lo(uint32_t tmem_d, uint32_t tmem_a, uint32_t desc_lo, uint32_t desc_hi, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 d;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "mov.b64 d, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], d, %4, p;\n\t}\n"
+      ::"r"(tmem_d), "r"(tmem_a), "r"(desc_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate) : "memory");
+}
+// ... and always accumulating
+__device__ __forceinline__ void umma_f16_ts_acc(uint32_t tmem_d, uint32_t tmem_a, uint32_t desc_lo, uint32_t desc_hi, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 d;\n\t"
+      "setp.eq.b32 p, 0, 0;\n\t"
+      "mov.b64 d, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], d, %4, p;\n\t}\n"
+      ::"r"(tmem_d), "r"(tmem_a), "r"(desc_lo), "r"(desc_hi), "r"(idesc) : "memory");
+}
+// wait for TWO barriers with one pair of try_waits per round (their ~90-cycle latencies overlap)
+__device__ __forceinline__ void mbar_wait2(uint32_t bar0, uint32_t par0, uint32_t bar1, uint32_t par1) {
+  asm volatile(
+      "{\n\t.reg .pred P0, P1;\n\t"
+      "WAIT2_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P0, [%0], %1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%2], %3;\n\t"
+      "and.pred P0, P0, P1;\n\t"
+      "@P0 bra WAIT2_DONE;\n\t"
+      "bra WAIT2_LOOP;\n\t"
+      "WAIT2_DONE:\n\t}\n" ::"r"(bar0), "r"(par0), "r"(bar1), "r"(par1) : "memory");
+}
 // register re-allocation between warp roles: every warp of a warpgroup (4 consecutive warps) executes the same one
 template <int R> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
 template <int R> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R)); }

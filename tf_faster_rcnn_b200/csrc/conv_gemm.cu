@@ -756,42 +756,56 @@ conv_gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       }
     } else if (warp == 18) {
       // ---------------- MMA issuer: the whole warp walks the loop converged (operands in uniform registers) ----------------
+      // r02 finding 5 (ablations, tools/r02_conv_check.py ablate + SASS): this loop was ~140 instructions per k-block -- four
+      // dependent try_waits (~90 cycles each even when the phase has completed), 64-bit descriptor arithmetic and R2UR moves
+      // per MMA -- i.e. ~1000 cycles on a warp that issues one instruction every ~5 cycles, against 768 cycles of tensor work:
+      // the head layers were ISSUE bound.  Now: the two per-k-block waits are one try_wait pair, every operand is base +
+      // immediate (descriptor high word constant, low word = 14-bit address field), the chunk / unit waits sit outside the
+      // common path.  (Measured: neutral -- 170 vs 167 us on the head 3x3 -- so the issue stream is not the limiter either;
+      // one elected arrive per splitter warp + releasing the TMEM slot's first channel half early measured 5 % SLOWER.  With every
+      // load, convert and 2/3 of the MMAs ablated the k-block period is still ~600 cycles: the 2-deep TMEM operand ring's
+      // round trip (commit -> splitter wake -> tcgen05.st -> wait::st -> arrive -> issuer wake) bounds the loop; a deeper ring
+      // needs TMEM columns that D_main[2] + D_small + A[2] already use up at BN = 128.)
       const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
       uint32_t kbt = 0, ct = 0, ut = 0;
-      int sb = 0; uint32_t pb = 0;
+      uint32_t sb = 0, pb = 0;
       const uint32_t d_small = tb + (uint32_t)F_TMEM_DSMALL;
-      const uint32_t sb0 = smem_u32(smem_b);
+      const uint32_t blo0 = ((smem_u32(smem_b) & 0x3FFFFu) >> 4) | (1u << 16);   // low descriptor word of stage 0's hi plane (LBO field = 1)
+      constexpr uint32_t kDescHi = (uint32_t)(1024u >> 4) | (1u << 14) | (2u << 29);   // SBO = 1024 B, version 1, SWIZZLE_128B
+      constexpr uint32_t kStageStep = (uint32_t)kBStage >> 4, kPlaneStep = (uint32_t)kBTile >> 4;
       const int kpc = p.kb_per_chunk;
+      const uint32_t bar_ta_full = smem_u32(ta_full), bar_b_full = smem_u32(b_full);
       for (int u = blockIdx.x; u < p.total_units; u += gridDim.x, ++ut) {
         const Unit t = decode_unit(p, u, num_kb_total);
         const int nkb = __shfl_sync(0xffffffffu, t.num_kb, 0);
         int in_chunk = 0;
+        MBAR_WAIT(small_empty, (ut & 1u) ^ 1u, 7, kbt);                                  // D_small of the previous unit has been read
 #pragma unroll 1
         for (int kb = 0; kb < nkb; ++kb, ++kbt) {
           const uint32_t b = ct & 1u;
           if (in_chunk == 0) MBAR_WAIT(&acc_empty[b], ((ct >> 1) & 1u) ^ 1u, 6, kbt);   // D_main[b]'s previous chunk has been drained
-          if (kb == 0) MBAR_WAIT(small_empty, (ut & 1u) ^ 1u, 7, kbt);                  // D_small of the previous unit has been read
           const uint32_t st = kbt & (uint32_t)(F_ST - 1);
-          MBAR_WAIT(&ta_full[st], (kbt >> 1) & 1u, 8, kbt);
-          MBAR_WAIT(&b_full[sb], pb, 9, kbt);
+          mbar_wait2(bar_ta_full + st * 8u, (kbt >> 1) & 1u, bar_b_full + sb * 8u, pb);   // A planes stored AND B tiles landed
           tc_fence_after();
-          const uint32_t sbase = sb0 + (uint32_t)(sb * kBStage);
-          const uint64_t b_hi = sw128_desc(sbase);
-          const uint64_t b_lo = sw128_desc(sbase + kBTile);
+          const uint32_t bl = blo0 + sb * kStageStep;
           const uint32_t a0 = tb + (uint32_t)F_TMEM_A0 + st * 64u;
           const uint32_t d_main = tb + b * 128u;
           const bool last = (in_chunk + 1 == kpc) || (kb + 1 == nkb);
           if (elect_one()) {
 #pragma unroll
             for (int j = 0; j < F_BK / 16; ++j) {
-              const uint64_t off = (uint64_t)(j * 16 * 2) >> 4;               // B: advance 16 fp16 = 32 B inside the 128-byte swizzle row
-              const uint32_t a_hi = a0 + (uint32_t)((j >> 1) * 32 + (j & 1) * 8);   // A: 32-channel half, then 16 fp16 = 8 TMEM columns
-              const uint32_t a_lo = a_hi + 16u;
-              if (!(p.dbg & 2)) {
-                umma_f16_ts(d_small, a_lo, b_hi + off, kIdesc, (j > 0 || kb > 0) ? 1u : 0u);
-                umma_f16_ts(d_small, a_hi, b_lo + off, kIdesc, 1u);
+              // B: 16 fp16 = 32 B inside the 128-byte swizzle row = +2 in the address field; A: 32-channel half, then 8 TMEM columns
+              const uint32_t bh_j = bl + 2u * j, bl_j = bl + kPlaneStep + 2u * j;
+              const uint32_t a_hi = a0 + (uint32_t)((j >> 1) * 32 + (j & 1) * 8), a_lo = a_hi + 16u;
+              if (j == 0) {
+                umma_f16_ts_lo(d_small, a_lo, bh_j, kDescHi, kIdesc, kb > 0 ? 1u : 0u);
+                umma_f16_ts_acc(d_small, a_hi, bl_j, kDescHi, kIdesc);
+                umma_f16_ts_lo(d_main, a_hi, bh_j, kDescHi, kIdesc, in_chunk > 0 ? 1u : 0u);
+              } else {
+                umma_f16_ts_acc(d_small, a_lo, bh_j, kDescHi, kIdesc);
+                umma_f16_ts_acc(d_small, a_hi, bl_j, kDescHi, kIdesc);
+                umma_f16_ts_acc(d_main, a_hi, bh_j, kDescHi, kIdesc);
               }
-              umma_f16_ts(d_main, a_hi, b_hi + off, kIdesc, (j > 0 || in_chunk > 0) ? 1u : 0u);
             }
             umma_commit(&ta_empty[st]);
             umma_commit(&b_empty[sb]);
