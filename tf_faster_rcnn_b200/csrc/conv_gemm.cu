@@ -561,6 +561,7 @@ constexpr int F_BK = 64;                                // channels per k-block 
 constexpr int F_SA = 3;                                 // smem ring of raw fp32 A stages (2 x 16 KiB each)
 constexpr int F_SB = 3;                                 // smem ring of B (hi | lo) fp16 stages
 constexpr int F_ST = 2;                                 // TMEM ring of split A tiles
+constexpr int F_RDY = 6;                                // 'operands ready' barriers: lcm(F_ST, F_SB)
 constexpr int F_A_STAGE = 2 * A_TILE_BYTES;
 constexpr int F_TMEM_DSMALL = 256, F_TMEM_A0 = 384;
 constexpr int F_REGS_SPLIT = 80, F_REGS_EPI = 136, F_REGS_CTRL = 40;
@@ -587,10 +588,13 @@ conv_gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   uint8_t* smem_stage = smem_b + F_SB * kBStage;        // epilogue transposition buffer
   uint64_t* a_full = reinterpret_cast<uint64_t*>(smem_stage + STAGE_BYTES);
   uint64_t* a_empty = a_full + F_SA;
-  uint64_t* b_full = a_empty + F_SA;
-  uint64_t* b_empty = b_full + F_SB;
-  uint64_t* ta_full = b_empty + F_SB;         // both splitter groups (256 threads) stored their halves into the TMEM slot
-  uint64_t* ta_empty = ta_full + F_ST;        // the MMAs reading the TMEM slot completed (tcgen05.commit)
+  // ready[kbt % 6]: k-block kbt's operands are complete -- the 256 splitter threads stored its A planes into the TMEM slot AND
+  // its B tiles landed (the B producer's arrive.expect_tx + the TMA bytes).  One barrier (6 = lcm of the 2-deep TMEM ring and
+  // the 3-deep B ring), so the MMA issuer pays ONE try_wait per k-block (r02 trace: a try_wait costs ~90-170 cycles of the
+  // single issuing warp even when the phase is already complete, and the tensor queue is too shallow to cover it).
+  uint64_t* ready = a_empty + F_SA;
+  uint64_t* b_empty = ready + F_RDY;
+  uint64_t* ta_empty = b_empty + F_SB;        // the MMAs reading the TMEM slot completed (tcgen05.commit)
   uint64_t* acc_full = ta_empty + F_ST;       // [2] D_main[b] holds a finished chunk partial (tcgen05.commit)
   uint64_t* acc_empty = acc_full + 2;         // [2] the epilogue warps have read D_main[b] (256 arrivals)
   uint64_t* small_empty = acc_empty + 2;      // the epilogue warps have read D_small of the finished unit (256 arrivals)
@@ -603,8 +607,9 @@ conv_gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   if (warp == 16 && lane == 0) {
     tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmBhi); tma_prefetch_desc(&tmBlo);
     for (int s = 0; s < F_SA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], F_SPLIT_THREADS); }
-    for (int s = 0; s < F_SB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-    for (int s = 0; s < F_ST; ++s) { mbar_init(&ta_full[s], F_SPLIT_THREADS); mbar_init(&ta_empty[s], 1); }
+    for (int s = 0; s < F_RDY; ++s) mbar_init(&ready[s], F_SPLIT_THREADS + 1);
+    for (int s = 0; s < F_SB; ++s) mbar_init(&b_empty[s], 1);
+    for (int s = 0; s < F_ST; ++s) mbar_init(&ta_empty[s], 1);
     for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], EPI_THREADS); }
     mbar_init(small_empty, EPI_THREADS);
     mbar_fence_init();
@@ -626,9 +631,11 @@ conv_gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     int total_kb = 0;                         // k-blocks of all units of this CTA (the splitter needs nothing else about them)
     for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) total_kb += decode_unit(p, u, num_kb_total).num_kb;
     int sa = 0; uint32_t pa = 0;
+    int r6 = 0;
 #pragma unroll 1
     for (int kbt = 0; kbt < total_kb; ++kbt) {
       MBAR_WAIT(&a_full[sa], pa, 1, kbt);
+      if (threadIdx.x == 0) FRCNN_TRACE(0, kbt);
       // SWIZZLE_128B: 16-byte chunk c of row r sits at chunk (c ^ (r & 7)); quarter-warp phases are conflict-free
       const uint8_t* arow = smem_a + sa * F_A_STAGE + g * A_TILE_BYTES + row * 128;
       uint32_t pk[32];                        // [0,16): hi pairs (k, k+1), [16,32): lo pairs
@@ -651,12 +658,16 @@ conv_gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       // while a load is still outstanding (the A producer re-fills the stage as soon as all 256 threads arrived)
       mbar_arrive_after(&a_empty[sa], (pk[0] | pk[2] | pk[4]) | (pk[6] | pk[8] | pk[10]) | (pk[12] | pk[14]));
       const int st = kbt & (F_ST - 1);
+      if (threadIdx.x == 0) FRCNN_TRACE(1, kbt);
       MBAR_WAIT(&ta_empty[st], (((uint32_t)kbt >> 1) & 1u) ^ 1u, 2, kbt);   // TMEM slot no longer read by the tensor core
+      if (threadIdx.x == 0) FRCNN_TRACE(2, kbt);
       tc_fence_after();
       tmem_st_32x32(tmem_base + lane_field + (uint32_t)(F_TMEM_A0 + st * 64 + g * 32), pk);
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(&ta_full[st]);
+      mbar_arrive(&ready[r6]);              // k-block kbt: this thread's part of the A planes is in tensor memory
+      if (threadIdx.x == 0) FRCNN_TRACE(3, kbt);
+      if (++r6 == F_RDY) r6 = 0;
       if (++sa == F_SA) { sa = 0; pa ^= 1u; }
     }
   } else if (warp < 16) {
@@ -679,6 +690,7 @@ conv_gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         const uint32_t b = ct & 1u;
         MBAR_WAIT(&acc_full[b], (ct >> 1) & 1u, 3, ct);
         tc_fence_after();
+        if (threadIdx.x == 256) FRCNN_TRACE(7, ct);
         if (c + 1 == num_chunks) {
           // the cross terms of the unit's whole k range (complete: this acc_full commit covered every MMA), scaled by 2^11.
           // Drained BEFORE the last chunk partial: D_small is single buffered, the next unit's first MMA waits for it.
@@ -739,18 +751,20 @@ conv_gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     } else if (warp == 17 && lane == 0) {
       // ---------------- TMA producer, weights (static data: runs ahead of the previous kernel's tail) ----------------
       int sb = 0; uint32_t pb = 0;
+      int r6 = 0;
       for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
         const Unit t = decode_unit(p, u, num_kb_total);
 #pragma unroll 1
         for (int kb = 0; kb < t.num_kb; ++kb) {
           const int kcoord = (t.kb0 + kb) * F_BK;                 // K axis of the packed weights = (tap, cin) flattened; past the end: zeros
           MBAR_WAIT(&b_empty[sb], pb ^ 1u, 5, kb);                // the MMAs that read this slot completed
-          if (p.dbg & 8) mbar_arrive(&b_full[sb]);
+          if (p.dbg & 8) mbar_arrive(&ready[r6]);
           else {
-            mbar_expect_tx(&b_full[sb], (uint32_t)kBStage);
-            tma_load_2d(smem_b + sb * kBStage, &tmBhi, &b_full[sb], kcoord, t.nblk * BN);
-            tma_load_2d(smem_b + sb * kBStage + kBTile, &tmBlo, &b_full[sb], kcoord, t.nblk * BN);
+            mbar_expect_tx(&ready[r6], (uint32_t)kBStage);
+            tma_load_2d(smem_b + sb * kBStage, &tmBhi, &ready[r6], kcoord, t.nblk * BN);
+            tma_load_2d(smem_b + sb * kBStage + kBTile, &tmBlo, &ready[r6], kcoord, t.nblk * BN);
           }
+          if (++r6 == F_RDY) r6 = 0;
           if (++sb == F_SB) { sb = 0; pb ^= 1u; }
         }
       }
@@ -761,20 +775,20 @@ conv_gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       // per MMA -- i.e. ~1000 cycles on a warp that issues one instruction every ~5 cycles, against 768 cycles of tensor work:
       // the head layers were ISSUE bound.  Now: the two per-k-block waits are one try_wait pair, every operand is base +
       // immediate (descriptor high word constant, low word = 14-bit address field), the chunk / unit waits sit outside the
-      // common path.  (Measured: neutral -- 170 vs 167 us on the head 3x3 -- so the issue stream is not the limiter either;
+      // common path (one try_wait on the joint `ready` barrier).  (Measured: neutral -- 170 vs 167 us on the head 3x3 -- so the issue stream is not the limiter either;
       // one elected arrive per splitter warp + releasing the TMEM slot's first channel half early measured 5 % SLOWER.  With every
       // load, convert and 2/3 of the MMAs ablated the k-block period is still ~600 cycles: the 2-deep TMEM operand ring's
       // round trip (commit -> splitter wake -> tcgen05.st -> wait::st -> arrive -> issuer wake) bounds the loop; a deeper ring
       // needs TMEM columns that D_main[2] + D_small + A[2] already use up at BN = 128.)
       const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
       uint32_t kbt = 0, ct = 0, ut = 0;
-      uint32_t sb = 0, pb = 0;
+      uint32_t sb = 0;
       const uint32_t d_small = tb + (uint32_t)F_TMEM_DSMALL;
       const uint32_t blo0 = ((smem_u32(smem_b) & 0x3FFFFu) >> 4) | (1u << 16);   // low descriptor word of stage 0's hi plane (LBO field = 1)
       constexpr uint32_t kDescHi = (uint32_t)(1024u >> 4) | (1u << 14) | (2u << 29);   // SBO = 1024 B, version 1, SWIZZLE_128B
       constexpr uint32_t kStageStep = (uint32_t)kBStage >> 4, kPlaneStep = (uint32_t)kBTile >> 4;
       const int kpc = p.kb_per_chunk;
-      const uint32_t bar_ta_full = smem_u32(ta_full), bar_b_full = smem_u32(b_full);
+      uint32_t r6 = 0, pr = 0;
       for (int u = blockIdx.x; u < p.total_units; u += gridDim.x, ++ut) {
         const Unit t = decode_unit(p, u, num_kb_total);
         const int nkb = __shfl_sync(0xffffffffu, t.num_kb, 0);
@@ -785,8 +799,10 @@ conv_gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           const uint32_t b = ct & 1u;
           if (in_chunk == 0) MBAR_WAIT(&acc_empty[b], ((ct >> 1) & 1u) ^ 1u, 6, kbt);   // D_main[b]'s previous chunk has been drained
           const uint32_t st = kbt & (uint32_t)(F_ST - 1);
-          mbar_wait2(bar_ta_full + st * 8u, (kbt >> 1) & 1u, bar_b_full + sb * 8u, pb);   // A planes stored AND B tiles landed
+          if (lane == 0) FRCNN_TRACE(4, kbt);
+          MBAR_WAIT(&ready[r6], pr, 8, kbt);                                             // A planes stored AND B tiles landed
           tc_fence_after();
+          if (lane == 0) FRCNN_TRACE(5, kbt);
           const uint32_t bl = blo0 + sb * kStageStep;
           const uint32_t a0 = tb + (uint32_t)F_TMEM_A0 + st * 64u;
           const uint32_t d_main = tb + b * 128u;
@@ -812,8 +828,10 @@ conv_gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             if (last) umma_commit(&acc_full[b]);
           }
           __syncwarp();
+          if (lane == 0) FRCNN_TRACE(6, kbt);
           if (last) { in_chunk = 0; ++ct; } else ++in_chunk;
-          if (++sb == F_SB) { sb = 0; pb ^= 1u; }
+          if (++sb == F_SB) sb = 0;
+          if (++r6 == F_RDY) { r6 = 0; pr ^= 1u; }
         }
       }
     }

@@ -16,7 +16,7 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."
 from tf_faster_rcnn_b200 import ops, _native as N  # noqa: E402
 
 F = np.float32
-TAGS = {1: "splitter:a_full", 2: "splitter:ta_empty", 3: "epilogue:acc_full", 4: "producerA:a_empty", 5: "producerB:b_empty",
+TAGS = {1: "splitter:a_full", 2: "splitter:ta_empty", 3: "epilogue:acc_full", 4: "producerA:a_empty", 5: "producerB:b_empty", 8: "mma:ready",
         6: "mma:acc_empty", 7: "mma:small_empty", 8: "mma:ta_full", 9: "mma:b_full"}
 
 
