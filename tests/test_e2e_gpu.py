@@ -304,6 +304,26 @@ def test_detect_batch_matches_oracle_per_image(cuda):
         assert rep["matched"] >= 0.95 * max(single.shape[0], 1) and rep["score_err"] < 1e-4
 
 
+def test_submit_collect_pipeline_equals_detect_batch(cuda):
+    """The pipelined throughput API (two batches in flight, copy stream + staging buffers) returns exactly detect_batch()'s records."""
+    import torch
+    net, w = build("res50", 21, (8, 16, 32))
+    hw = (208, 320)
+    batches = [np.concatenate([synth.synthetic_blob(hw[0], hw[1], 10 * i + b) for b in range(2)], axis=0) for i in range(5)]
+    metas = [([1.0 + 0.1 * i, 0.9], [(208, 320), (231, 355)]) for i in range(5)]
+    want = [net.detect_batch(x, m[0], m[1])[0] for x, m in zip(batches, metas)]
+    pinned = [torch.from_numpy(x).pin_memory() for x in batches]
+    tickets, got = [], []
+    for x, m in zip(pinned, metas):
+        tickets.append(net.submit_batch(x, m[0], m[1]))
+        if len(tickets) > 1:
+            got.append(net.collect_batch(tickets.pop(0)))
+    got.append(net.collect_batch(tickets.pop(0)))
+    for g, wnt in zip(got, want):
+        for a, b in zip(g, wnt):
+            assert np.array_equal(a, b)
+
+
 def test_plan_cache_is_bounded(cuda):
     """the per-shape plan cache is an LRU (hundreds of distinct blob shapes in a dataset must not exhaust HBM)."""
     net, w = build("res50", 21, (8, 16, 32))

@@ -243,9 +243,12 @@ class ShapePlan:
         # ---- im_detect tail on the device (test.py:95-107): per-image (scale, orig_h, orig_w) live in im_meta --------------
         self.pred_boxes = t.new(B * R, 4 * C)
         self.im_meta = t.new(B, 3)
-        self.im_meta_host = torch.empty((B, 3), dtype=torch.float32).pin_memory() if torch.cuda.is_available() else torch.empty((B, 3))
-        self.im_meta_host[:] = torch.tensor([1.0, float(h), float(w)])
-        self.im_meta.copy_(self.im_meta_host)
+        # pinned staging for the meta rows: a ring, because the H2D copies are asynchronous and the host may already be
+        # preparing the launch after next (submit_batch keeps two batches in flight)
+        self.im_meta_ring = [torch.empty((B, 3), dtype=torch.float32).pin_memory() for _ in range(4)]
+        self.im_meta_turn = 0
+        self.im_meta_ring[0][:] = torch.tensor([1.0, float(h), float(w)])
+        self.im_meta.copy_(self.im_meta_ring[0])
         t.add("bbox_decode", lambda: ops.bbox_decode(self.rois, self.bbox_pred, C, self.im_meta, self.pred_boxes))
         self.n_im_detect_steps = len(t.steps)
         # ---- test_net tail (test.py:162-180): built on first use for the options in force (_ensure_post) ---------------------
@@ -321,9 +324,11 @@ class ShapePlan:
 
     def set_meta(self, rows):
         """rows: per image (im_scale, orig_h, orig_w); staged in pinned memory, copied on the launching stream."""
+        self.im_meta_turn = (self.im_meta_turn + 1) & 3
+        host = self.im_meta_ring[self.im_meta_turn]
         for b, (s, oh, ow) in enumerate(rows):
-            self.im_meta_host[b, 0] = float(F(s)); self.im_meta_host[b, 1] = float(oh); self.im_meta_host[b, 2] = float(ow)
-        self.im_meta.copy_(self.im_meta_host, non_blocking=True)
+            host[b, 0] = float(F(s)); host[b, 1] = float(oh); host[b, 2] = float(ow)
+        self.im_meta.copy_(host, non_blocking=True)
 
     def launch(self, im_scale=1.0, orig_h=None, orig_w=None, post=False, detect=False, meta=None):
         """Enqueue one batch (inputs already in self.image) on the current stream.  meta: per-image (scale, orig_h, orig_w)
@@ -357,16 +362,20 @@ class ShapePlan:
 
     def records(self):
         """Host copy of the detection records of the batch after a 'detect' launch: list of [n,6] arrays (one D2H copy)."""
-        host = self.rec.cpu()
-        counts = host.view(torch.int32)[:, 0].numpy()
-        out = []
-        for b in range(self.batch):
-            n = int(counts[b])
-            if n > self.max_det:
-                raise RuntimeError("image %d of the batch produced %d detections but the record buffer holds %d "
-                                   "(score ties beyond the max_per_image head-room)" % (b, n, self.max_det))
-            out.append(host[b, REC_HEADER:REC_HEADER + n * 6].view(n, 6).numpy().copy())
-        return out
+        return split_host_records(self.rec.cpu(), self.max_det)
+
+
+def split_host_records(host, max_det):
+    """host: CPU float32 tensor [B, REC_HEADER + max_det*6] -> list of [n,6] numpy arrays; raises when a record set did not fit."""
+    counts = host.view(torch.int32)[:, 0].numpy()
+    out = []
+    for b in range(host.shape[0]):
+        n = int(counts[b])
+        if n > max_det:
+            raise RuntimeError("image %d of the batch produced %d detections but the record buffer holds %d "
+                               "(score ties beyond the max_per_image head-room)" % (b, n, max_det))
+        out.append(host[b, REC_HEADER:REC_HEADER + n * 6].view(n, 6).numpy().copy())
+    return out
 
 
 def nms_threshold(thresh, use_gpu_nms):

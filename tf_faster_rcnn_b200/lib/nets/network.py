@@ -165,3 +165,45 @@ class Network(object):
         self._copy_in(plan, images)
         plan.launch(post=True, detect=True, meta=[(float(im_scales[i]), int(orig_hws[i][0]), int(orig_hws[i][1])) for i in range(b)])
         return plan.records(), plan
+
+    # ---- pipelined throughput API: overlap the next batch's host->device copy with the current batch's compute ---------------
+    def submit_batch(self, images, im_scales, orig_hws):
+        """Enqueue one batch without waiting for it: the H2D copy of `images` (a PINNED torch tensor or a numpy array, [B,H,W,3])
+        runs on a copy stream into one of two staging buffers, the compute stream picks it up behind an event, replays the graph
+        and copies the records into one of two pinned host buffers.  -> ticket for collect_batch().  At most TWO tickets may be
+        outstanding (submit i+1, collect i, submit i+2, ...): that is what keeps the copy of batch i+1 under the compute of
+        batch i.  Results are identical to detect_batch()."""
+        b = int(images.shape[0])
+        assert images.shape[3] == 3 and len(im_scales) == b and len(orig_hws) == b
+        plan = self.plan_for(images.shape[1], images.shape[2], b)
+        pipe = plan.__dict__.setdefault("_pipe", None)
+        if pipe is None:
+            pipe = plan._pipe = dict(copy_stream=torch.cuda.Stream(), stage=[torch.empty_like(plan.image) for _ in range(2)],
+                                     staged=[torch.cuda.Event() for _ in range(2)], consumed=[torch.cuda.Event() for _ in range(2)],
+                                     done=[torch.cuda.Event() for _ in range(2)], host=[None, None], turn=0, used=[False, False])
+        k = pipe["turn"] & 1
+        pipe["turn"] += 1
+        src = images if isinstance(images, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(images, dtype=np.float32))
+        main = torch.cuda.current_stream()
+        with torch.cuda.stream(pipe["copy_stream"]):
+            if pipe["used"][k]:
+                pipe["copy_stream"].wait_event(pipe["consumed"][k])     # the compute stream has taken the previous content of stage k
+            pipe["stage"][k].copy_(src, non_blocking=True)
+            pipe["staged"][k].record(pipe["copy_stream"])
+        main.wait_event(pipe["staged"][k])
+        plan.image.copy_(pipe["stage"][k], non_blocking=True)             # device-to-device: ~microseconds, keeps the graph's input address fixed
+        pipe["consumed"][k].record(main)
+        pipe["used"][k] = True
+        plan.launch(post=True, detect=True, meta=[(float(im_scales[i]), int(orig_hws[i][0]), int(orig_hws[i][1])) for i in range(b)])
+        if pipe["host"][k] is None or pipe["host"][k].shape != plan.rec.shape:
+            pipe["host"][k] = torch.empty(plan.rec.shape, dtype=torch.float32).pin_memory()
+        pipe["host"][k].copy_(plan.rec, non_blocking=True)
+        pipe["done"][k].record(main)
+        return (plan, k, plan.max_det)
+
+    def collect_batch(self, ticket):
+        """Wait for a submitted batch -> list of B det arrays [n,6]."""
+        plan, k, max_det = ticket
+        pipe = plan._pipe
+        pipe["done"][k].synchronize()
+        return engine.split_host_records(pipe["host"][k], max_det)
