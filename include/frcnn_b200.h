@@ -60,7 +60,8 @@ int frcnn_check_device(int device_id);
 /* ---- (1) NMS, host buffers: replaces `_nms` (lib/nms/gpu_nms.hpp:1-2, nms_kernel.cu:91-144) ----------
  * boxes_host: [boxes_num, boxes_dim>=4] rows (x1,y1,x2,y2,...), ALREADY sorted by descending score, as the
  * reference's Cython wrapper guarantees (gpu_nms.pyx:25-28).  keep_out: capacity boxes_num; receives
- * indices into the sorted input in ascending order.  Synchronous. */
+ * indices into the sorted input in ascending order.  Synchronous.  device_id < 0 selects the calling thread's current
+ * device; the caller's current device is restored before returning (the reference's _nms leaves it switched). */
 int frcnn_nms_host(int* keep_out, int* num_out, const float* boxes_host, int boxes_num, int boxes_dim,
                    float nms_overlap_thresh, int device_id, unsigned flags);
 

@@ -322,3 +322,22 @@ def test_nms_module_surface_routes_to_the_device_entry(monkeypatch):
     assert calls[-1][1] == float(np.nextafter(np.float32(0.7), np.float32(1)))    # f32(0.7) < 0.7: next fp32 up
     assert py_cpu_nms(dets, 0.3) == [1, 2] and calls[-1][2] == N.NMS_MODE_GPU_NMS
     assert gpu_nms(np.zeros((0, 5), np.float32), 0.3) == [] and cpu_nms(np.zeros((0, 5), np.float32), 0.3) == []
+
+
+def test_bbox_transform_module_matches_oracle_codec():
+    """model.bbox_transform (reference module surface): decode / clip equal the oracle codec on fp32 inputs up to exp's last ulp,
+    the regression targets invert the decode."""
+    from model import bbox_transform as BT
+    from oracle import boxes as OB
+    rng = np.random.default_rng(4)
+    b = np.sort(rng.uniform(0, 500, (50, 2, 2)), axis=1).transpose(0, 2, 1).reshape(50, 4).astype(np.float32)[:, [0, 2, 1, 3]]
+    b = np.stack([b[:, 0], b[:, 1], b[:, 0] + rng.uniform(5, 200, 50), b[:, 1] + rng.uniform(5, 200, 50)], axis=1).astype(np.float32)
+    d = (rng.standard_normal((50, 12)) * 0.3).astype(np.float32)
+    got = BT.bbox_transform_inv(b, d)
+    want = OB.decode(b, d)
+    assert got.dtype == np.float32 and np.abs(got - want).max() < 1e-3 * 1.0 and np.abs(got - want).max() / np.abs(want).max() < 1e-6
+    assert np.array_equal(BT.clip_boxes(got.copy(), (375, 500)), OB.clip_two_sided(got, 375, 500))
+    assert BT.bbox_transform_inv(np.zeros((0, 4), np.float32), np.zeros((0, 8), np.float32)).shape == (0, 8)
+    # targets: '+1' widths, centre offsets in units of the example box, log size ratios (hand-computed case)
+    t = BT.bbox_transform(np.array([[0., 0., 9., 9.]]), np.array([[5., 5., 24., 24.]]))
+    assert np.allclose(t, [[1.0, 1.0, np.log(2.0), np.log(2.0)]])

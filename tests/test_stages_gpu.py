@@ -435,3 +435,39 @@ def test_detect_post_top_mode_5000_rois(cuda):
     want_flat = np.vstack([np.hstack([d, np.full((d.shape[0], 1), j, F)]) for j, d in enumerate(want) if d.shape[0]])
     assert nd == want_flat.shape[0]
     assert np.array_equal(det.cpu().numpy()[:nd], want_flat)
+
+
+def test_reference_proposal_layer_modules(cuda):
+    """layer_utils.proposal_layer / proposal_layer_tf / proposal_top_layer(_tf): the reference's array-in / array-out entry points,
+    device sort + NMS underneath, against the oracle's three proposal modes."""
+    from model.config import cfg
+    from layer_utils.proposal_layer import proposal_layer, proposal_layer_tf
+    from layer_utils.proposal_top_layer import proposal_top_layer, proposal_top_layer_tf
+    A, fh, fw = 9, 20, 30
+    rng = np.random.default_rng(9)
+    cls = (rng.standard_normal((1, fh, fw, 2 * A)) * 2).astype(F)
+    box = (rng.standard_normal((1, fh, fw, 4 * A)) * 0.3).astype(F)
+    im_info = np.array([320, 480, 1.0], F)
+    o = P.opts()
+    prob = np.concatenate([1 - P.rpn_fg_prob(cls).reshape(1, fh, fw, A), P.rpn_fg_prob(cls).reshape(1, fh, fw, A)], axis=3).astype(F)
+    scores, props, anchors = P.rpn_decode(cls, box, im_info, o)
+    saved = (cfg.USE_GPU_NMS, cfg.TEST.RPN_TOP_N)
+    try:
+        cfg.USE_GPU_NMS = False
+        blob, sc = proposal_layer(prob, box, im_info, "TEST", 16, anchors, A)
+        want_rois, want_sc, _ = P.proposals_numpy(scores, props, P.opts(use_e2e_tf=False, use_gpu_nms=False))
+        assert blob.shape == want_rois.shape and np.abs(blob - want_rois).max() < 1e-3 and np.abs(sc - want_sc).max() < 1e-6
+        blob, sc = proposal_layer_tf(prob, box, im_info, "TEST", 16, anchors, A)
+        want_rois, want_sc, _ = P.proposals_e2e_tf(scores, props, o)
+        assert blob.shape == want_rois.shape and np.abs(blob - want_rois).max() < 1e-3 and np.abs(sc - want_sc).max() < 1e-6
+        cfg.TEST.RPN_TOP_N = 2000
+        blob, sc = proposal_top_layer_tf(prob, box, im_info, 16, anchors, A)
+        want_rois, want_sc, _ = P.proposals_top(scores, props, P.opts(test_mode="top", rpn_top_n=2000))
+        assert blob.shape == (2000, 5) and np.abs(blob - want_rois).max() < 1e-3
+        blob2, _ = proposal_top_layer(prob, box, im_info, 16, anchors, A)
+        assert np.array_equal(blob, blob2)
+        cfg.TEST.RPN_TOP_N = 6000                      # more than the 5400 anchors: random fill with replacement, as the reference
+        blob3, sc3 = proposal_top_layer(prob, box, im_info, 16, anchors, A)
+        assert blob3.shape == (6000, 5) and sc3.shape == (6000, 1)
+    finally:
+        cfg.USE_GPU_NMS, cfg.TEST.RPN_TOP_N = saved

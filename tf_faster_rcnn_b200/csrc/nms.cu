@@ -416,26 +416,32 @@ extern "C" int frcnn_proposals(const float* props, const float* scores, const in
   return OK;
 }
 
-// workspace for the global kept set, grown on demand (per process, single stream use)
-static float4* g_kept = nullptr; static float* g_kept_area = nullptr; static int g_kept_cap = 0;
-static int ensure_kept(int n) {
-  if (n <= g_kept_cap) return OK;
-  if (g_kept) { cudaFree(g_kept); cudaFree(g_kept_area); g_kept = nullptr; g_kept_area = nullptr; g_kept_cap = 0; }
-  FRCNN_CUDA(cudaMalloc(&g_kept, (size_t)n * sizeof(float4)));
-  FRCNN_CUDA(cudaMalloc(&g_kept_area, (size_t)n * sizeof(float)));
-  g_kept_cap = n;
+// Kept-set workspace of the `_nms`-compatible path: one slot PER DEVICE (a process-wide buffer was reused on
+// whatever device a later call named), grown on demand; single stream use per device.
+constexpr int MAX_DEVICES = 64;
+static float4* g_kept[MAX_DEVICES]; static float* g_kept_area[MAX_DEVICES]; static int g_kept_cap[MAX_DEVICES];
+static int ensure_kept(int dev, int n) {
+  FRCNN_REQUIRE(dev >= 0 && dev < MAX_DEVICES, "device index %d out of range", dev);
+  if (n <= g_kept_cap[dev]) return OK;
+  if (g_kept[dev]) { cudaFree(g_kept[dev]); cudaFree(g_kept_area[dev]); g_kept[dev] = nullptr; g_kept_area[dev] = nullptr; g_kept_cap[dev] = 0; }
+  FRCNN_CUDA(cudaMalloc(&g_kept[dev], (size_t)n * sizeof(float4)));
+  FRCNN_CUDA(cudaMalloc(&g_kept_area[dev], (size_t)n * sizeof(float)));
+  g_kept_cap[dev] = n;
   return OK;
 }
 
 extern "C" int frcnn_nms_sorted_dev(const float* boxes, int n, float thresh, unsigned flags, int max_out, int* keep, int* num, void* stream) {
   FRCNN_REQUIRE(boxes && keep && num && n > 0 && max_out > 0, "nms_sorted_dev: bad argument");
-  int rc = ensure_kept(max_out < n ? max_out : n);
+  int dev = 0;
+  FRCNN_CUDA(cudaGetDevice(&dev));
+  int rc = ensure_kept(dev, max_out < n ? max_out : n);
   if (rc) return rc;
-  nms_sorted_kernel<<<1, NMS_THREADS, 0, (cudaStream_t)stream>>>(boxes, 4, n, thresh, flags, max_out, g_kept, g_kept_area, keep, num);
+  nms_sorted_kernel<<<1, NMS_THREADS, 0, (cudaStream_t)stream>>>(boxes, 4, n, thresh, flags, max_out, g_kept[dev], g_kept_area[dev], keep, num);
   FRCNN_LAUNCH_CHECK();
   return OK;
 }
 
+// device_id < 0: the calling thread's current device.  The caller's current device is restored before returning.
 extern "C" int frcnn_nms_host(int* keep_out, int* num_out, const float* boxes_host, int boxes_num, int boxes_dim, float thresh,
                               int device_id, unsigned flags) {
   FRCNN_REQUIRE(keep_out && num_out, "nms_host: null output");
@@ -444,23 +450,28 @@ extern "C" int frcnn_nms_host(int* keep_out, int* num_out, const float* boxes_ho
   FRCNN_REQUIRE(boxes_host && boxes_dim >= 4, "nms_host: bad input");
   int cur = -1;
   FRCNN_CUDA(cudaGetDevice(&cur));
-  if (cur != device_id) FRCNN_CUDA(cudaSetDevice(device_id));
+  const int dev = device_id < 0 ? cur : device_id;
+  if (cur != dev) FRCNN_CUDA(cudaSetDevice(dev));
   float* dboxes = nullptr; int* dkeep = nullptr; int* dnum = nullptr;
-  int rc = ensure_kept(boxes_num);
+  int rc = ensure_kept(dev, boxes_num);
+  cudaError_t e = cudaSuccess;
+  if (!rc) {
+    e = cudaMalloc(&dboxes, (size_t)boxes_num * boxes_dim * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&dkeep, (size_t)(boxes_num + 1) * sizeof(int));
+    if (e == cudaSuccess) {
+      dnum = dkeep + boxes_num;
+      e = cudaMemcpy(dboxes, boxes_host, (size_t)boxes_num * boxes_dim * sizeof(float), cudaMemcpyHostToDevice);
+    }
+    if (e == cudaSuccess) {
+      nms_sorted_kernel<<<1, NMS_THREADS>>>(dboxes, boxes_dim, boxes_num, thresh, flags, boxes_num, g_kept[dev], g_kept_area[dev], dkeep, dnum);
+      e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(num_out, dnum, sizeof(int), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && *num_out > 0) e = cudaMemcpy(keep_out, dkeep, (size_t)(*num_out) * sizeof(int), cudaMemcpyDeviceToHost);
+    cudaFree(dboxes); cudaFree(dkeep);
+  }
+  if (cur != dev) cudaSetDevice(cur);                    // leave the caller's (torch's) current device untouched
   if (rc) return rc;
-  cudaError_t e = cudaMalloc(&dboxes, (size_t)boxes_num * boxes_dim * sizeof(float));
-  if (e == cudaSuccess) e = cudaMalloc(&dkeep, (size_t)(boxes_num + 1) * sizeof(int));
-  if (e == cudaSuccess) {
-    dnum = dkeep + boxes_num;
-    e = cudaMemcpy(dboxes, boxes_host, (size_t)boxes_num * boxes_dim * sizeof(float), cudaMemcpyHostToDevice);
-  }
-  if (e == cudaSuccess) {
-    nms_sorted_kernel<<<1, NMS_THREADS>>>(dboxes, boxes_dim, boxes_num, thresh, flags, boxes_num, g_kept, g_kept_area, dkeep, dnum);
-    e = cudaGetLastError();
-  }
-  if (e == cudaSuccess) e = cudaMemcpy(num_out, dnum, sizeof(int), cudaMemcpyDeviceToHost);
-  if (e == cudaSuccess && *num_out > 0) e = cudaMemcpy(keep_out, dkeep, (size_t)(*num_out) * sizeof(int), cudaMemcpyDeviceToHost);
-  cudaFree(dboxes); cudaFree(dkeep);
   if (e != cudaSuccess) return cuda_fail(e, "frcnn_nms_host", __FILE__, __LINE__);
   return OK;
 }

@@ -33,7 +33,8 @@ class AttrDict(dict):
     __setattr__ = __setitem__
 
 
-_ROOT = osp.abspath(osp.join(osp.dirname(__file__), "..", ".."))
+# the REPOSITORY root (three levels above lib/model/): data/, output/ live next to tools/ as in the reference layout
+_ROOT = osp.abspath(osp.join(osp.dirname(__file__), "..", "..", ".."))
 
 cfg = AttrDict(
     TRAIN=dict(

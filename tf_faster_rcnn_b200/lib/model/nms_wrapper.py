@@ -17,5 +17,5 @@ def nms(dets, thresh, force_cpu=False):
     dets = np.ascontiguousarray(dets, dtype=np.float32)
     order = np.argsort(-dets[:, 4], kind="stable")
     t32, flags = engine.nms_threshold(thresh, bool(cfg.USE_GPU_NMS) and not force_cpu)
-    keep = ops.nms_host(dets[order], t32, flags, device_id=0)
+    keep = ops.nms_host(dets[order], t32, flags, device_id=-1)   # the process's current device (rank-local under torchrun)
     return list(order[keep])

@@ -12,5 +12,5 @@ def cpu_nms(dets, thresh):
         return []
     order = np.argsort(-dets[:, 4], kind="stable")
     t32, flags = engine.nms_threshold(thresh, False)
-    keep = ops.nms_host(dets[order], t32, flags, device_id=0)
+    keep = ops.nms_host(dets[order], t32, flags, device_id=-1)
     return list(order[keep])

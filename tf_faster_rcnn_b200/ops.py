@@ -226,8 +226,8 @@ def nms_sorted_dev(boxes, thresh, flags, max_out, keep, num):
                                          _stream()), "nms_sorted_dev")
 
 
-def nms_host(sorted_dets, thresh, flags, device_id=0):
-    """`_nms`-compatible call on HOST arrays (already sorted by descending score)."""
+def nms_host(sorted_dets, thresh, flags, device_id=-1):
+    """`_nms`-compatible call on HOST arrays (already sorted by descending score).  device_id < 0: the current device."""
     d = np.ascontiguousarray(sorted_dets, dtype=np.float32)
     n = d.shape[0]
     keep = np.empty(max(n, 1), dtype=np.int32)
