@@ -242,6 +242,13 @@ __device__ __forceinline__ float ld_nc_f32_pinned(const float* p) {
   return v;
 }
 
+// 128-bit load from a 32-bit shared-space address
+__device__ __forceinline__ float4 lds_f4(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
+
 // programmatic dependent launch: let the next kernel in the stream start its prologue early / wait for the previous one's data
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }

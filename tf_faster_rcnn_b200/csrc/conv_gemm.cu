@@ -84,6 +84,10 @@ struct ConvKernelParams {
                       // the hi*hi product, 4 / 8 producer A / B skip their TMA, 16 epilogue skips the chunk promotion loads.  0 in production.
 };
 
+// clock64 stamps of CTA 0's pipeline hand-offs: compiled in only in the development build (libfrcnn_b200_wd.so, -DFRCNN_WATCHDOG);
+// in the production library the macros vanish (r02: the stamp sites cost ~5 instructions each -- 20 per k-block on a splitter
+// warp, 15 on the MMA-issuing warp, both of which bound the k-block period).
+#ifdef FRCNN_WATCHDOG
 #define FRCNN_TRACE2(base, idx)                                                             \
   do {                                                                                      \
     if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && (idx) < 64) p.trace[(base) + (idx)] = clock64(); \
@@ -92,6 +96,10 @@ struct ConvKernelParams {
   do {                                                                                      \
     if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && (kbv) < 64) p.trace[(kbv) * 8 + (slot)] = clock64(); \
   } while (0)
+#else
+#define FRCNN_TRACE2(base, idx) do { } while (0)
+#define FRCNN_TRACE(slot, kbv) do { } while (0)
+#endif
 
 constexpr int STAGE_BYTES = 8 * 32 * 32 * 4;          // epilogue transposition buffer: 8 warps x 32 rows x 32 columns fp32
 template <int BN> constexpr int b_stage_bytes() { return 2 * BN * BLOCK_K * 4; }
@@ -632,12 +640,18 @@ conv_gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) total_kb += decode_unit(p, u, num_kb_total).num_kb;
     int sa = 0; uint32_t pa = 0;
     int r6 = 0;
+    // SWIZZLE_128B: 16-byte chunk c of row r sits at chunk (c ^ (r & 7)); quarter-warp phases are conflict-free.  The eight
+    // chunk addresses of this thread's row are loop invariants up to the stage offset (32-bit shared-space addresses: the
+    // generic-pointer form cost ~40 address instructions per k-block).
+    const uint32_t arow0 = smem_u32(smem_a) + (uint32_t)(g * A_TILE_BYTES + row * 128);
+    uint32_t coff[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) coff[c] = arow0 + (uint32_t)((c ^ (row & 7)) << 4);
 #pragma unroll 1
     for (int kbt = 0; kbt < total_kb; ++kbt) {
       MBAR_WAIT(&a_full[sa], pa, 1, kbt);
       if (threadIdx.x == 0) FRCNN_TRACE(0, kbt);
-      // SWIZZLE_128B: 16-byte chunk c of row r sits at chunk (c ^ (r & 7)); quarter-warp phases are conflict-free
-      const uint8_t* arow = smem_a + sa * F_A_STAGE + g * A_TILE_BYTES + row * 128;
+      const uint32_t stage_off = (uint32_t)(sa * F_A_STAGE);
       uint32_t pk[32];                        // [0,16): hi pairs (k, k+1), [16,32): lo pairs
       if (p.dbg & 1) {
 #pragma unroll
@@ -645,7 +659,7 @@ conv_gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       } else {
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-          const float4 v = *reinterpret_cast<const float4*>(arow + ((c ^ (row & 7)) << 4));
+          const float4 v = lds_f4(coff[c] + stage_off);
           const uint32_t h01 = pack_f16x2_sat(v.x, v.y), h23 = pack_f16x2_sat(v.z, v.w);
           const float2 f01 = __half22float2(*reinterpret_cast<const __half2*>(&h01));
           const float2 f23 = __half22float2(*reinterpret_cast<const __half2*>(&h23));

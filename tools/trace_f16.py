@@ -1,4 +1,4 @@
-"""Debug aid (GPU box): clock64 timeline of CTA 0's pipeline hand-offs in conv_gemm_f16x3_kernel for its first 64 k-blocks.
+"""Debug aid (GPU box; needs the development build: FRCNN_LIB_VARIANT=wd python tools/trace_f16.py): clock64 timeline of CTA 0's pipeline hand-offs in conv_gemm_f16x3_kernel for its first 64 k-blocks.
 
 columns per k-block: S0 splitter saw a_full | S1 converted (starts waiting ta_empty) | S2 got ta_empty | S3 arrived ta_full |
 M4 issuer starts waiting | M5 operands ready | M6 MMAs issued + committed ; per chunk: E7 epilogue saw acc_full"""
