@@ -43,11 +43,14 @@ __global__ void pack_weights_f16_kernel(const float* __restrict__ w, __half* __r
 }
 
 // ---- first-layer convolution, cin == 3 ------------------------------------------------------------------
-// Block = 8x16 output pixels x all output channels.  The input patch and the whole filter bank sit in shared memory;
-// a warp = 32 pixels x one group of 32 output channels, so every weight read is a warp-wide broadcast float4 and each
-// thread keeps 32 accumulators (1 input LDS + 8 weight LDS.128 per 32 FFMA).
-constexpr int CF_TH = 8, CF_TW = 16;
-__global__ void __launch_bounds__(256)
+// Block = CF_TH x CF_TW output pixels x all output channels.  The input patch and the whole filter bank sit in shared memory;
+// a warp = 32 lanes x PIX pixels each x one group of 32 output channels, so every weight read is a warp-wide broadcast float4
+// and each thread keeps 32 * PIX accumulators.  r02: with PIX = 1 the loop issued 9 LDS per 32 FFMA (1 input + 8 weight float4)
+// and was bound by the shared-memory pipe (ncu: SM 43 %, 21 TFLOP/s of fp32); PIX = 2 reuses every weight float4 for two pixels
+// (10 LDS per 64 FFMA).  The accumulation order per output is unchanged (taps in (r, s, c) order, one fmaf each).
+constexpr int CF_TH = 8, CF_TW = 32;
+template <int PIX>
+__global__ void __launch_bounds__(256, PIX == 2 ? 2 : 1)
 conv_first_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ scale,
                   const float* __restrict__ shift, float* __restrict__ out, int h, int wd, int cout, int k, int stride,
                   int pad_t, int pad_l, int ho, int wo, int act, int tiles_x, int tiles_y) {
@@ -70,43 +73,59 @@ conv_first_kernel(const float* __restrict__ in, const float* __restrict__ w, con
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int groups = cout >> 5;                           // 32-channel groups (1 or 2)
   const int g = warp % groups;
-  const int pblk = warp / groups;                         // 32-pixel block inside the tile
+  const int pblk = warp / groups;                         // block of 32 * PIX pixels inside the tile
   const int nblk = (blockDim.x >> 5) / groups;
-  for (int pb = pblk; pb < (CF_TH * CF_TW) / 32; pb += nblk) {
-    const int pix = pb * 32 + lane;
-    const int py = pix / CF_TW, px = pix % CF_TW;
-    float acc[32];
+  for (int pb = pblk; pb < (CF_TH * CF_TW) / (32 * PIX); pb += nblk) {
+    int py[PIX], px[PIX];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+    for (int q = 0; q < PIX; ++q) {
+      const int pix = pb * 32 * PIX + q * 32 + lane;
+      py[q] = pix / CF_TW; px[q] = pix % CF_TW;
+    }
+    float acc[PIX][32];
+#pragma unroll
+    for (int q = 0; q < PIX; ++q)
+#pragma unroll
+      for (int i = 0; i < 32; ++i) acc[q][i] = 0.f;
     for (int r = 0; r < k; ++r)
       for (int s2 = 0; s2 < k; ++s2) {
-        const float* ip = psm + ((py * stride + r) * pw + px * stride + s2) * 3;
+        const float* ip[PIX];
+#pragma unroll
+        for (int q = 0; q < PIX; ++q) ip[q] = psm + ((py[q] * stride + r) * pw + px[q] * stride + s2) * 3;
         const float* wp = wsm + ((r * k + s2) * 3) * cout + g * 32;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-          const float x = ip[c];
+          float x[PIX];
+#pragma unroll
+          for (int q = 0; q < PIX; ++q) x[q] = ip[q][c];
           const float4* w4 = reinterpret_cast<const float4*>(wp + c * cout);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float4 wv = w4[j];
-            acc[4 * j + 0] = fmaf(x, wv.x, acc[4 * j + 0]); acc[4 * j + 1] = fmaf(x, wv.y, acc[4 * j + 1]);
-            acc[4 * j + 2] = fmaf(x, wv.z, acc[4 * j + 2]); acc[4 * j + 3] = fmaf(x, wv.w, acc[4 * j + 3]);
+#pragma unroll
+            for (int q = 0; q < PIX; ++q) {
+              acc[q][4 * j + 0] = fmaf(x[q], wv.x, acc[q][4 * j + 0]); acc[q][4 * j + 1] = fmaf(x[q], wv.y, acc[q][4 * j + 1]);
+              acc[q][4 * j + 2] = fmaf(x[q], wv.z, acc[q][4 * j + 2]); acc[q][4 * j + 3] = fmaf(x[q], wv.w, acc[q][4 * j + 3]);
+            }
           }
         }
       }
-    const int oy = oy0 + py, ox = ox0 + px;
-    if (oy < ho && ox < wo) {
-      float* op = out + (((size_t)b * ho + oy) * wo + ox) * cout + g * 32;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        float v = acc[i];
-        const int ch = g * 32 + i;
-        if (scale) v = __fmul_rn(v, __ldg(scale + ch));
-        if (shift) v = __fadd_rn(v, __ldg(shift + ch));
-        acc[i] = apply_act(v, act);
+    for (int q = 0; q < PIX; ++q) {
+      const int oy = oy0 + py[q], ox = ox0 + px[q];
+      if (oy < ho && ox < wo) {
+        float* op = out + (((size_t)b * ho + oy) * wo + ox) * cout + g * 32;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float v = acc[q][i];
+          const int ch = g * 32 + i;
+          if (scale) v = __fmul_rn(v, __ldg(scale + ch));
+          if (shift) v = __fadd_rn(v, __ldg(shift + ch));
+          acc[q][i] = apply_act(v, act);
+        }
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(op + i) = make_float4(acc[q][i], acc[q][i + 1], acc[q][i + 2], acc[q][i + 3]);
       }
-#pragma unroll
-      for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(op + i) = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
     }
   }
 }
@@ -438,12 +457,18 @@ extern "C" int frcnn_conv_first(const float* in, const float* w, const float* sc
   FRCNN_REQUIRE(smem <= 100 * 1024, "conv_first: %zu B of shared memory needed", smem);
   static size_t attr_smem = 0;
   if (smem > 48 * 1024 && smem > attr_smem) {
-    FRCNN_CUDA(cudaFuncSetAttribute(conv_first_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FRCNN_CUDA(cudaFuncSetAttribute(conv_first_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FRCNN_CUDA(cudaFuncSetAttribute(conv_first_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_smem = smem;
   }
   const int tiles_x = cdiv(wo, CF_TW), tiles_y = cdiv(ho, CF_TH);
-  conv_first_kernel<<<(unsigned)(tiles_x * tiles_y * n), 256, smem, (cudaStream_t)stream>>>(in, w, scale, shift, out, h, wd, cout, k, stride,
-                                                                                         pad_t, pad_l, ho, wo, act, tiles_x, tiles_y);
+  const unsigned grid = (unsigned)(tiles_x * tiles_y * n);
+  if (cout == 64)       // 2 channel groups x 4 pixel blocks of 64 = the 8 warps, two pixels per thread
+    conv_first_kernel<2><<<grid, 256, smem, (cudaStream_t)stream>>>(in, w, scale, shift, out, h, wd, cout, k, stride, pad_t, pad_l, ho, wo, act,
+                                                                   tiles_x, tiles_y);
+  else                  // cout == 32: 8 pixel blocks of 32, one pixel per thread
+    conv_first_kernel<1><<<grid, 256, smem, (cudaStream_t)stream>>>(in, w, scale, shift, out, h, wd, cout, k, stride, pad_t, pad_l, ho, wo, act,
+                                                                   tiles_x, tiles_y);
   FRCNN_LAUNCH_CHECK();
   return OK;
 }
