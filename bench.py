@@ -38,6 +38,14 @@ NETS = {
 }
 
 
+def make_config(label, net_name, batch, world, rec_bytes=None):
+    """The `config` object of the JSON line: identical for both arms (the CPU arm times single images of the same workload)."""
+    return {"workload": label, "net": net_name, "images_per_step_per_gpu": batch, "parallelism": "image-sharded dp%d" % world,
+            "l2": "per-step working set (weight planes + activations of %d image(s), > 1 GB) exceeds the 126 MB L2; no explicit flush" % batch,
+            "final_nms": "cpu_nms predicate (USE_GPU_NMS=False)", "rpn": "proposal_layer_tf semantics (USE_E2E_TF=True)",
+            "collective": "one async all_gather_into_tensor of the record buffer per step" if world > 1 else "none"}
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -139,7 +147,8 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "images/sec", "value": v, "unit": "images/s", "n_gpus": args.gpus, "steps": steps,
             "steps_requested": args.steps, "warmup": warm, "ms_per_step": 1000 * dt / steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": label, "impl_note": "TF1 unavailable offline: CPU port (oracle) of the reference path, torch-CPU fp32 convs"},
+            "config": make_config(label, args.net, max(1, int(args.batch)), args.gpus),
+            "impl_note": "TF1 unavailable offline: CPU port (oracle) of the reference path, torch-CPU fp32 convs; one image per timed step",
             "cpu_baseline": {"value": v, "unit": "images/s", "cores": cores, "kind": "port", "sample": "1 image of the bench workload per step; %d of %d requested steps timed (%.0f s budget)" % (steps, args.steps, budget_s)},
             "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -366,10 +375,7 @@ def run_ours(args):
         "ms_per_step": ms / n_steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f16x3 (fp32-grade: fp16 hi/lo split of both operands, 3 tcgen05 kind::f16 MMAs per product, fp32 accumulate)",
         "data": "synthetic",
-        "config": {"workload": label, "net": args.net, "images_per_step_per_gpu": B, "parallelism": "image-sharded dp%d" % world,
-                   "l2": "per-step working set (weight planes + activations of %d images, > 1 GB) exceeds the 126 MB L2; no explicit flush" % B,
-                   "final_nms": "cpu_nms predicate (USE_GPU_NMS=False)", "rpn": "proposal_layer_tf semantics (USE_E2E_TF=True)",
-                   "collective": "one async all_gather_into_tensor of the %d-byte record buffer per step" % rec_bytes if world > 1 else "none"},
+        "config": make_config(label, args.net, B, world, rec_bytes),
         "e2e": {"value": e2e_v, "unit": "images/s", "h2d_bytes_per_step": int(host_blob.numel() * 4 + B * 12), "d2h_bytes_per_step": int(rec_bytes),
                 "ms_per_step": ms_e2e / n_steps, "api": "Network.submit_batch(pinned host blobs) / collect_batch() -> per-image detection records on the host, two batches in flight"},
         "gpu_launches": launches_per_step * n_steps,
