@@ -793,7 +793,8 @@ conv_gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       // one elected arrive per splitter warp + releasing the TMEM slot's first channel half early measured 5 % SLOWER.  With every
       // load, convert and 2/3 of the MMAs ablated the k-block period is still ~600 cycles: the 2-deep TMEM operand ring's
       // round trip (commit -> splitter wake -> tcgen05.st -> wait::st -> arrive -> issuer wake) bounds the loop; a deeper ring
-      // needs TMEM columns that D_main[2] + D_small + A[2] already use up at BN = 128.)
+      // needs TMEM columns that D_main[2] + D_small + A[2] already use up at BN = 128.  Two issuing warps alternating k-blocks
+      // behind an mbarrier order token (tcgen05 fences on both sides) also measured neutral -- 175.7 vs 174.5 us -- and is not kept.)
       const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
       uint32_t kbt = 0, ct = 0, ut = 0;
       uint32_t sb = 0;
