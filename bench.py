@@ -56,17 +56,49 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """SM clock, power and throttle reasons sampled while the timed region runs: NVML every 20 ms (the driver's 20-step runs last
+    ~0.2 s), falling back to `nvidia-smi` every ~150 ms when the NVML binding is unavailable."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    MASKS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
+        self.index, self.rows, self.stop_flag, self.source = index, [], False, "nvidia-smi"
+        self.nvml = self.handle = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml, self.source = pynvml, "nvml"
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n, h = self.nvml, self.handle
+        sm = float(n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM))
+        try:
+            mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(h))
+        except Exception:
+            mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+        try:
+            power = n.nvmlDeviceGetPowerUsage(h) / 1000.0
+        except Exception:
+            power = float("nan")
+        flags = ["Active" if mask & self.MASKS[nm] else "Not Active" for nm in self.NAMES]
+        return [str(sm), str(self.max_mhz), str(power)] + flags
 
     def run(self):
         while not self.stop_flag:
             try:
+                if self.nvml is not None:
+                    self.rows.append(self._sample_nvml())
+                    time.sleep(0.02)
+                    continue
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
                 if out:
@@ -76,16 +108,21 @@ class ClockSampler(threading.Thread):
             time.sleep(0.1)
 
     def summary(self):
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        def num(v):
+            try:
+                return float(v)
+            except ValueError:
+                return None
+        sm = [num(r[0]) for r in self.rows if r and num(r[0]) is not None]
+        mx = [num(r[1]) for r in self.rows if len(r) > 1 and num(r[1]) is not None]
+        pw = [num(r[2]) for r in self.rows if len(r) > 2 and num(r[2]) is not None and num(r[2]) == num(r[2])]
         reasons = set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
-            for i, nm in enumerate(names):
+            for i, nm in enumerate(self.NAMES):
                 if len(r) > 3 + i and r[3 + i].lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(self.rows)}
+                "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons), "samples": len(self.rows), "source": self.source}
 
 
 def make_inputs(net_name, seed=3):
@@ -155,6 +192,8 @@ def run_reference(args):
 
 
 def run_ours(args):
+    if args.precision == "f16x1":
+        os.environ["FRCNN_CONV_IMPL"] = "f16x1"
     import torch
     import torch.distributed as dist
     from tf_faster_rcnn_b200 import _native
@@ -373,7 +412,10 @@ def run_ours(args):
     line = {
         "metric": "images/sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": n_steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms / n_steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f16x3 (fp32-grade: fp16 hi/lo split of both operands, 3 tcgen05 kind::f16 MMAs per product, fp32 accumulate)",
+        "dtype": ("f16x3 (fp32-grade: fp16 hi/lo split of both operands, 3 tcgen05 kind::f16 MMAs per product, fp32 accumulate)"
+                  if args.precision != "f16x1" else
+                  "f16x1 THROUGHPUT MODE -- reduced precision (plain fp16 operands, fp32 accumulate), NOT the parity path and NOT the "
+                  "headline: deviation from the oracle in profiles/r02_parity.md"),
         "data": "synthetic",
         "config": make_config(label, args.net, B, world, rec_bytes),
         "e2e": {"value": e2e_v, "unit": "images/s", "h2d_bytes_per_step": int(host_blob.numel() * 4 + B * 12), "d2h_bytes_per_step": int(rec_bytes),
@@ -417,6 +459,8 @@ def main():
     ap.add_argument("--net", default="res101", choices=sorted(NETS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-lib-peaks", action="store_true", help="skip the two 8192^3 library matmuls timed for context after the run")
+    ap.add_argument("--precision", default="fp32-grade", choices=["fp32-grade", "f16x1"],
+                    help="f16x1 = the opt-in THROUGHPUT mode (plain fp16 operands, fp32 accumulate): NOT the parity path, its line says so")
     ap.add_argument("--batch", type=int, default=int(os.environ.get("FRCNN_BENCH_BATCH", "4")),
                     help="images per GPU per step (one graph replay); 1 = the reference's batch size")
     ap.add_argument("--layers", action="store_true", help="print a per-launch CUDA-event timing table of one image (eager, warm) and exit")

@@ -79,6 +79,8 @@ int frcnn_nms_sorted_dev(const float* boxes_dev, int n, float thresh, unsigned f
 typedef struct frcnn_conv_plan frcnn_conv_plan;
 #define FRCNN_CONV_F16X3 0   /* fp16 hi/lo split of both operands, 3 x tcgen05.mma.kind::f16, fp32 accumulate */
 #define FRCNN_CONV_TF32X3 1  /* tf32 hi/lo split, 3 x kind::tf32 (same 22-bit products, twice the tensor time) */
+#define FRCNN_CONV_F16X1 2   /* THROUGHPUT mode, not fp32-grade: plain fp16 operands (the hi planes only), 1 MMA per product, fp32
+                              * accumulate; ~3e-4 of the output range per layer instead of ~4e-7.  Same packed weights as F16X3. */
 
 typedef struct {
   const float* in_dev;       /* [n, h, w, cin] */
@@ -96,7 +98,7 @@ typedef struct {
   int block_n;               /* 0 = choose; else 64/128 */
   int kb_per_chunk;          /* 0 = default (8): 32-wide k-blocks summed in TMEM before promotion to registers */
   int split_k;               /* 0 = choose; 1 = never; n = split the K loop over n CTAs + deterministic reduce pass */
-  int impl;                  /* FRCNN_CONV_F16X3 (0, default) | FRCNN_CONV_TF32X3 (r01 kernel, kept for A/B measurements) */
+  int impl;                  /* FRCNN_CONV_F16X3 (0, default) | FRCNN_CONV_TF32X3 (r01 kernel, kept for A/B measurements) | FRCNN_CONV_F16X1 */
   float out_mult;            /* F16X3: 2^-wexp of frcnn_pack_conv_weights (0 is read as 1) */
 } frcnn_conv_desc;
 

@@ -149,3 +149,25 @@ def test_split_k(cuda, shape):
               (name, sk, info["splits"], info["grid_m"], info["grid_n"], info["block_n"], e, info["us"]))
         assert e < 5e-6
         assert np.array_equal(got, got2), "split-K must be run-to-run deterministic"
+
+
+def test_throughput_mode_f16x1(cuda):
+    """FRCNN_CONV_F16X1 (opt-in, NOT fp32-grade): plain fp16 operands, one MMA per product, fp32 accumulation -- error of a few
+    1e-4 of the output range, three orders above the default FP16x3 path on the same packed weights."""
+    from tf_faster_rcnn_b200 import ops, _native as N
+    rng = np.random.default_rng(12)
+    for (n, h, w, cin, cout, k) in [(1, 38, 50, 256, 256, 3), (20, 7, 7, 512, 512, 1), (1, 1, 300, 3136, 128, 1)]:
+        x = np.maximum(rng.standard_normal((n, h, w, cin)), 0).astype(np.float32)
+        wt = (rng.standard_normal((k, k, cin, cout)) * np.sqrt(2.0 / (k * k * cin))).astype(np.float32)
+        ho, wo, pt, pl = ops.conv_out_hw(h, w, k, 1, "SAME")
+        errs = {}
+        for impl in (N.CONV_F16X3, N.CONV_F16X1):
+            pc = ops.PackedConv(wt, impl=impl)
+            out = torch.full((n, ho, wo, cout), float("nan"), dtype=torch.float32, device="cuda")
+            ops.ConvPlan(torch.from_numpy(x).cuda(), pc, out, 1, pt, pl, 0, None).run()
+            torch.cuda.synchronize()
+            errs[impl] = out.cpu().numpy()
+        scale = np.abs(errs[N.CONV_F16X3]).max()
+        dev = np.abs(errs[N.CONV_F16X1] - errs[N.CONV_F16X3]).max() / scale
+        assert not np.isnan(errs[N.CONV_F16X1]).any()
+        assert 1e-6 < dev < 3e-3, dev

@@ -335,3 +335,28 @@ def test_plan_cache_is_bounded(cuda):
         assert len(net._plans) <= 2
     for x, y in zip(outs[0], outs[3]):           # evicted and rebuilt: same results
         assert np.array_equal(x, y)
+
+
+def test_throughput_mode_end_to_end_deviation(cuda, monkeypatch):
+    """Opt-in throughput mode (FRCNN_CONV_IMPL=f16x1: plain fp16 operands, NOT fp32-grade) through the whole net: the deviation
+    from the oracle is REPORTED (profiles/r02_parity.md), bounded loosely here; the default path's 1e-4 bounds do not apply."""
+    monkeypatch.setenv("FRCNN_CONV_IMPL", "f16x1")
+    net, w = build("res50", 21, (8, 16, 32))
+    hw = (320, 480)
+    blob = synth.synthetic_blob(*hw)
+    im_info = np.array([hw[0], hw[1], 1.0], F)
+    st = P.test_image("res50", w, blob, im_info, 21, P.opts())
+    cls_score, cls_prob, bbox_pred, rois = net.test_image(None, blob, im_info)
+    plan = net.plan_for(*hw)
+    e_feat = relerr(plan.feat.cpu().numpy(), st["feat"])
+    keep = plan.roi_keep.cpu().numpy()[:rois.shape[0]]
+    common, ia, ib = np.intersect1d(keep, st["roi_keep"], return_indices=True)
+    e_prob = float(np.abs(cls_prob[ia] - st["cls_prob"][ib]).max()) if len(common) else float("nan")
+    det, _ = net.detect(blob, im_info, hw)
+    scores, boxes = P.im_detect_post(st["rois"], st["cls_prob"], st["bbox_pred"], 1.0, hw[0], hw[1])
+    rep = compare_detections(det, P.test_net_post(scores, boxes, P.opts()), tol=2.0)
+    line = ("[THROUGHPUT MODE f16x1 (not fp32-grade), res50 320x480] feature map rel err %.2e | RoIs common %d/%d | cls_prob abs %.2e | %s"
+            % (e_feat, len(common), len(st["roi_keep"]), e_prob, fmt_report(rep)))
+    print("\n" + line); parity_log(line)
+    assert 1e-5 < e_feat < 2e-2                       # visibly NOT the fp32-grade path, but sane
+    assert len(common) >= 0.7 * len(st["roi_keep"]) and rep["matched"] >= 0.6 * rep["n_want"]

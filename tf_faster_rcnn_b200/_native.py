@@ -15,7 +15,7 @@ NMS_MODE_CPU_NMS = NMS_PLUS_ONE | NMS_INCLUSIVE
 NMS_MODE_GPU_NMS = NMS_PLUS_ONE
 NMS_MODE_TF = NMS_SKIP_DEGENERATE
 ACT_NONE, ACT_RELU, ACT_RELU6 = 0, 1, 2
-CONV_F16X3, CONV_TF32X3 = 0, 1
+CONV_F16X3, CONV_TF32X3, CONV_F16X1 = 0, 1, 2
 
 vp, ci, cf, cu, sz = C.c_void_p, C.c_int, C.c_float, C.c_uint, C.c_size_t
 ip, fp = C.POINTER(C.c_int), C.POINTER(C.c_float)

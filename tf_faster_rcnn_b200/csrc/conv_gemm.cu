@@ -579,7 +579,9 @@ template <int BN> constexpr int f_smem_bytes() {
   return F_SA * F_A_STAGE + F_SB * 2 * f_b_tile_bytes<BN>() + STAGE_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
 }
 
-template <int BN>
+// X1 = throughput mode (FRCNN_CONV_F16X1, NOT fp32-grade): plain fp16 operands -- only the hi planes of A and B, ONE MMA per
+// k-slice, fp32 accumulate with the same chunked promotion; D_small, the lo planes and their loads / conversions are skipped.
+template <int BN, bool X1>
 __global__ void __launch_bounds__(F_THREADS, 1)
 conv_gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
                        const __grid_constant__ CUtensorMap tmBlo, const ConvKernelParams p) {
@@ -664,8 +666,12 @@ conv_gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           const float2 f01 = __half22float2(*reinterpret_cast<const __half2*>(&h01));
           const float2 f23 = __half22float2(*reinterpret_cast<const __half2*>(&h23));
           pk[2 * c] = h01; pk[2 * c + 1] = h23;
-          pk[16 + 2 * c] = pack_f16x2_sat(__fmul_rn(__fsub_rn(v.x, f01.x), 2048.f), __fmul_rn(__fsub_rn(v.y, f01.y), 2048.f));
-          pk[16 + 2 * c + 1] = pack_f16x2_sat(__fmul_rn(__fsub_rn(v.z, f23.x), 2048.f), __fmul_rn(__fsub_rn(v.w, f23.y), 2048.f));
+          if (!X1) {
+            pk[16 + 2 * c] = pack_f16x2_sat(__fmul_rn(__fsub_rn(v.x, f01.x), 2048.f), __fmul_rn(__fsub_rn(v.y, f01.y), 2048.f));
+            pk[16 + 2 * c + 1] = pack_f16x2_sat(__fmul_rn(__fsub_rn(v.z, f23.x), 2048.f), __fmul_rn(__fsub_rn(v.w, f23.y), 2048.f));
+          } else {
+            pk[16 + 2 * c] = 0u; pk[16 + 2 * c + 1] = 0u;
+          }
         }
       }
       // raw tile consumed: the arrive carries a data dependency on every one of the 8 row loads, so it cannot be issued
@@ -676,7 +682,8 @@ conv_gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       MBAR_WAIT(&ta_empty[st], (((uint32_t)kbt >> 1) & 1u) ^ 1u, 2, kbt);   // TMEM slot no longer read by the tensor core
       if (threadIdx.x == 0) FRCNN_TRACE(2, kbt);
       tc_fence_after();
-      tmem_st_32x32(tmem_base + lane_field + (uint32_t)(F_TMEM_A0 + st * 64 + g * 32), pk);
+      if (X1) tmem_st_32x16(tmem_base + lane_field + (uint32_t)(F_TMEM_A0 + st * 64 + g * 32), pk);   // hi pairs only
+      else tmem_st_32x32(tmem_base + lane_field + (uint32_t)(F_TMEM_A0 + st * 64 + g * 32), pk);
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&ready[r6]);              // k-block kbt: this thread's part of the A planes is in tensor memory
@@ -705,7 +712,7 @@ conv_gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         MBAR_WAIT(&acc_full[b], (ct >> 1) & 1u, 3, ct);
         tc_fence_after();
         if (threadIdx.x == 256) FRCNN_TRACE(7, ct);
-        if (c + 1 == num_chunks) {
+        if (!X1 && c + 1 == num_chunks) {
           // the cross terms of the unit's whole k range (complete: this acc_full commit covered every MMA), scaled by 2^11.
           // Drained BEFORE the last chunk partial: D_small is single buffered, the next unit's first MMA waits for it.
 #pragma unroll
@@ -774,9 +781,9 @@ conv_gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           MBAR_WAIT(&b_empty[sb], pb ^ 1u, 5, kb);                // the MMAs that read this slot completed
           if (p.dbg & 8) mbar_arrive(&ready[r6]);
           else {
-            mbar_expect_tx(&ready[r6], (uint32_t)kBStage);
+            mbar_expect_tx(&ready[r6], (uint32_t)(X1 ? kBTile : kBStage));
             tma_load_2d(smem_b + sb * kBStage, &tmBhi, &ready[r6], kcoord, t.nblk * BN);
-            tma_load_2d(smem_b + sb * kBStage + kBTile, &tmBlo, &ready[r6], kcoord, t.nblk * BN);
+            if (!X1) tma_load_2d(smem_b + sb * kBStage + kBTile, &tmBlo, &ready[r6], kcoord, t.nblk * BN);
           }
           if (++r6 == F_RDY) r6 = 0;
           if (++sb == F_SB) { sb = 0; pb ^= 1u; }
@@ -808,7 +815,7 @@ conv_gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         const Unit t = decode_unit(p, u, num_kb_total);
         const int nkb = __shfl_sync(0xffffffffu, t.num_kb, 0);
         int in_chunk = 0;
-        MBAR_WAIT(small_empty, (ut & 1u) ^ 1u, 7, kbt);                                  // D_small of the previous unit has been read
+        if (!X1) MBAR_WAIT(small_empty, (ut & 1u) ^ 1u, 7, kbt);                        // D_small of the previous unit has been read
 #pragma unroll 1
         for (int kb = 0; kb < nkb; ++kb, ++kbt) {
           const uint32_t b = ct & 1u;
@@ -829,12 +836,16 @@ conv_gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
               const uint32_t bh_j = bl + 2u * j, bl_j = bl + kPlaneStep + 2u * j;
               const uint32_t a_hi = a0 + (uint32_t)((j >> 1) * 32 + (j & 1) * 8), a_lo = a_hi + 16u;
               if (j == 0) {
-                umma_f16_ts_lo(d_small, a_lo, bh_j, kDescHi, kIdesc, kb > 0 ? 1u : 0u);
-                umma_f16_ts_acc(d_small, a_hi, bl_j, kDescHi, kIdesc);
+                if (!X1) {
+                  umma_f16_ts_lo(d_small, a_lo, bh_j, kDescHi, kIdesc, kb > 0 ? 1u : 0u);
+                  umma_f16_ts_acc(d_small, a_hi, bl_j, kDescHi, kIdesc);
+                }
                 umma_f16_ts_lo(d_main, a_hi, bh_j, kDescHi, kIdesc, in_chunk > 0 ? 1u : 0u);
               } else {
-                umma_f16_ts_acc(d_small, a_lo, bh_j, kDescHi, kIdesc);
-                umma_f16_ts_acc(d_small, a_hi, bl_j, kDescHi, kIdesc);
+                if (!X1) {
+                  umma_f16_ts_acc(d_small, a_lo, bh_j, kDescHi, kIdesc);
+                  umma_f16_ts_acc(d_small, a_hi, bl_j, kDescHi, kIdesc);
+                }
                 umma_f16_ts_acc(d_main, a_hi, bh_j, kDescHi, kIdesc);
               }
             }
@@ -968,7 +979,7 @@ struct frcnn_conv_plan {
   CUtensorMap tmA, tmBhi, tmBlo;
   ConvKernelParams kp;
   int block_n, stages, smem;
-  int impl;                // FRCNN_CONV_F16X3 | FRCNN_CONV_TF32X3
+  int impl;                // FRCNN_CONV_F16X3 | FRCNN_CONV_TF32X3 | FRCNN_CONV_F16X1
   dim3 grid;
   int n_tail;
   float* ws;               // owned workspace of the split tiles 
@@ -1028,11 +1039,11 @@ static int launch(const frcnn_conv_plan* p, cudaStream_t st) {
   return OK;
 }
 
-template <int BN>
+template <int BN, bool X1>
 static int launch_f16(const frcnn_conv_plan* p, cudaStream_t st) {
   static bool attr_done = false;
   if (!attr_done) {
-    FRCNN_CUDA(cudaFuncSetAttribute(conv_gemm_f16x3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, f_smem_bytes<BN>()));
+    FRCNN_CUDA(cudaFuncSetAttribute(conv_gemm_f16x3_kernel<BN, X1>, cudaFuncAttributeMaxDynamicSharedMemorySize, f_smem_bytes<BN>()));
     attr_done = true;
   }
   cudaLaunchAttribute attr[1];
@@ -1042,7 +1053,7 @@ static int launch_f16(const frcnn_conv_plan* p, cudaStream_t st) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = p->grid; cfg.blockDim = dim3(F_THREADS); cfg.dynamicSmemBytes = f_smem_bytes<BN>(); cfg.stream = st;
   cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
-  FRCNN_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_f16x3_kernel<BN>, p->tmA, p->tmBhi, p->tmBlo, p->kp));
+  FRCNN_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_f16x3_kernel<BN, X1>, p->tmA, p->tmBhi, p->tmBlo, p->kp));
   if (p->n_tail > 0) {
     cudaLaunchConfig_t rc{};
     rc.gridDim = dim3((unsigned)(p->n_tail * (BLOCK_M / (256 / (BN / 4))))); rc.blockDim = dim3(256); rc.dynamicSmemBytes = 0; rc.stream = st;
@@ -1213,7 +1224,7 @@ extern "C" int frcnn_conv_plan_create(frcnn_conv_plan** out, const frcnn_conv_de
   }
   p->grid = dim3((unsigned)g.grid, 1, 1);
   p->block_n = bn;
-  p->impl = f16 ? FRCNN_CONV_F16X3 : FRCNN_CONV_TF32X3;
+  p->impl = f16 ? (d->impl == FRCNN_CONV_F16X1 ? FRCNN_CONV_F16X1 : FRCNN_CONV_F16X3) : FRCNN_CONV_TF32X3;
   p->stages = f16 ? F_SA : RING;
   p->smem = f16 ? (bn == 128 ? f_smem_bytes<128>() : f_smem_bytes<64>()) : (bn == 128 ? smem_bytes<128>() : smem_bytes<64>());
   *out = p;
@@ -1223,7 +1234,8 @@ extern "C" int frcnn_conv_plan_create(frcnn_conv_plan** out, const frcnn_conv_de
 extern "C" int frcnn_conv_plan_run(const frcnn_conv_plan* p, void* stream) {
   FRCNN_REQUIRE(p, "null plan");
   cudaStream_t st = (cudaStream_t)stream;
-  if (p->impl == FRCNN_CONV_F16X3) return p->block_n == 128 ? launch_f16<128>(p, st) : launch_f16<64>(p, st);
+  if (p->impl == FRCNN_CONV_F16X3) return p->block_n == 128 ? launch_f16<128, false>(p, st) : launch_f16<64, false>(p, st);
+  if (p->impl == FRCNN_CONV_F16X1) return p->block_n == 128 ? launch_f16<128, true>(p, st) : launch_f16<64, true>(p, st);
   return p->block_n == 128 ? launch<128>(p, st) : launch<64>(p, st);
 }
 

@@ -32,8 +32,9 @@ def same_pads(n, k, s):
 
 
 def conv_impl():
-    """Dense-kernel generation: FP16x3 (default) or the r01 TF32x3 kernel (FRCNN_CONV_IMPL=tf32, A/B measurements)."""
-    return N.CONV_TF32X3 if os.environ.get("FRCNN_CONV_IMPL", "f16") == "tf32" else N.CONV_F16X3
+    """Dense-kernel arithmetic (FRCNN_CONV_IMPL): 'f16' = FP16x3, fp32-grade (default); 'tf32' = the r01 TF32x3 kernel (A/B
+    measurements); 'f16x1' = THROUGHPUT mode, plain fp16 operands with fp32 accumulation (NOT fp32-grade: ~3e-4 per layer)."""
+    return {"tf32": N.CONV_TF32X3, "f16x1": N.CONV_F16X1}.get(os.environ.get("FRCNN_CONV_IMPL", "f16"), N.CONV_F16X3)
 
 
 def weight_exponent(w):
@@ -56,7 +57,7 @@ class PackedConv:
         self.kh, self.kw, self.cin, self.cout = (int(v) for v in w.shape)
         ktot = self.kh * self.kw * self.cin
         self.impl = conv_impl() if impl is None else impl
-        if self.impl == N.CONV_F16X3:
+        if self.impl in (N.CONV_F16X3, N.CONV_F16X1):
             self.wexp = weight_exponent(wnp)
             self.out_mult = float(np.ldexp(1.0, -self.wexp))
             self.w_hi = torch.empty((self.cout, ktot), dtype=torch.float16, device="cuda")
