@@ -70,7 +70,7 @@ int frcnn_nms_host(int* keep_out, int* num_out, const float* boxes_host, int box
 int frcnn_nms_sorted_dev(const float* boxes_dev, int n, float thresh, unsigned flags, int max_out,
                          int* keep_dev, int* num_dev, void* stream);
 
-/* ---- (2) dense stages: conv / FC as implicit GEMM on tcgen05 (3xTF32, fp32 accumulate in TMEM) --------
+/* ---- (2) dense stages: conv / FC as implicit GEMM on tcgen05 (FP16x3 operand split, fp32 accumulate in TMEM) -
  * Replaces slim.conv2d / slim.fully_connected (+ folded bias or BatchNorm scale/shift, ReLU/ReLU6,
  * residual add) as used by lib/nets/{vgg16,resnet_v1,mobilenet_v1}.py and network.py:323-378.
  *   out[n,ho,wo,co] = act( (sum_{r,s,ci} in[n, ho*stride+r-pad_t, wo*stride+s-pad_l, ci] * w[co,r,s,ci])

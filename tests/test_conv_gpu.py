@@ -1,4 +1,4 @@
-"""Parity of the tcgen05 implicit-GEMM conv/FC kernel (3xTF32) against the oracle's fp32 CPU conv and a
+"""Parity of the tcgen05 implicit-GEMM conv/FC kernel (FP16x3; the r01 3xTF32 kernel via impl=1) against the oracle's fp32 CPU conv and a
 float64 reference.  Tolerance: the GPU result must be as close to the float64 truth as fp32 arithmetic allows
 (<= 4e-6 of the output's max magnitude; the fp32 oracle itself sits at ~1e-6) -- written per test."""
 import numpy as np

@@ -2,7 +2,7 @@
 TEST-mode graph on identical seeded weights and inputs.
 
 Stage-isolated tests (test_conv_gpu.py, test_stages_gpu.py) carry the bit-exact / 1e-4 claims.  End to end,
-two different fp32 summation orders (oneDNN on the CPU, tcgen05 3xTF32 on the GPU) feed a sort + greedy NMS,
+two different fp32 summation orders (oneDNN on the CPU, tcgen05 FP16x3 on the GPU) feed a sort + greedy NMS,
 so a near-tie may legitimately flip; the assertions below therefore check (a) every dense tensor to a
 relative bound, (b) the RoI set, (c) final scores/boxes to 1e-4 on the RoIs both sides selected."""
 import numpy as np

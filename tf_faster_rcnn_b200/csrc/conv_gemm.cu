@@ -2,6 +2,11 @@
 //   slim.conv2d 3x3 / 1x1 (any stride), slim.fully_connected  (lib/nets/vgg16.py:26-60,
 //   resnet_v1 bottlenecks, mobilenet pointwise, lib/nets/network.py:323-378)
 //
+// This file holds two generations of that kernel.  The one in production is conv_gemm_f16x3_kernel (r02, second half of the
+// file: its own header comment describes it); the r01 kernel below, conv_gemm_tf32x3_kernel, is kept behind
+// FRCNN_CONV_TF32X3 for A/B measurements.  What follows is the r01 design, which the r02 kernel inherits (implicit GEMM over
+// TMA boxes, A operand in tensor memory, two-level accumulation, persistent units, split-K).
+//
 // Math: D[M=pixels, N=cout] = sum over (filter tap, cin chunk) A_tap[M, 32] * W[N, 32]^T, fp32-grade via the
 // 3xTF32 split  a*b ~= a_lo*b_hi + a_hi*b_lo + a_hi*b_hi  (hi = RN_tf32(x), lo = RN_tf32(x - hi)),
 // accumulated in fp32 in TMEM by tcgen05.mma.kind::tf32.
