@@ -8,7 +8,7 @@
  * path is TensorFlow graph ops called from Python (lib/nets/network.py).  This header therefore exports
  *   (1) frcnn_nms_host      -- argument-compatible superset of `_nms` (same order + `flags`),
  *   (2) one entry point per device stage of the TEST-mode graph, so the Python host code that mirrors
- *       lib/nets/*.py can enqueue the graph on a CUDA stream (and capture it into a CUDA graph).
+ *       lib/nets/{vgg16,resnet_v1,mobilenet_v1}.py can enqueue the graph on a CUDA stream (and capture it into a CUDA graph).
  *
  * Conventions
  *   - plain C types only; every function returns 0 on success or a negative frcnn_status; the message of

@@ -87,3 +87,20 @@ def test_product_package_never_imports_the_oracle():
                     if re.search(r"^\s*(from\s+oracle\b|import\s+oracle\b)", src, flags=re.M):
                         offenders.append(os.path.join(d, f))
     assert offenders == []
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """include/frcnn_b200.h compiles as C99 (-pedantic, no warnings) and examples/nms_from_c.c -- the `_nms` call a C / Cython
+    maintainer would write -- links against the library and runs: version + empty-input call succeed without
+    a device; with a B200 present the 4-box call must keep boxes 0 and 2, without one it must fail with a message."""
+    import subprocess
+    exe = str(tmp_path / "nms_from_c")
+    libdir = os.path.join(ROOT, "tf_faster_rcnn_b200")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I" + os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "examples", "nms_from_c.c"), "-L" + libdir, "-lfrcnn_b200", "-Wl,-rpath," + libdir, "-o", exe],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "empty input: status 0, kept 0" in r.stdout
+    assert ("kept 2: 0 2" in r.stdout) or ("status -" in r.stdout)
