@@ -56,6 +56,8 @@ int frcnn_version(void);
 int frcnn_last_error(char* buf, size_t buflen);
 /* 0 when device `device_id` exists and is compute capability 10.x */
 int frcnn_check_device(int device_id);
+/* cudaMemsetAsync(dev_ptr, 0, bytes) on `stream`: lets a host layer clear buffers (detection records) without a framework fill kernel */
+int frcnn_zero_async(void* dev_ptr, size_t bytes, void* stream);
 
 /* ---- (1) NMS, host buffers: replaces `_nms` (lib/nms/gpu_nms.hpp:1-2, nms_kernel.cu:91-144) ----------
  * boxes_host: [boxes_num, boxes_dim>=4] rows (x1,y1,x2,y2,...), ALREADY sorted by descending score, as the

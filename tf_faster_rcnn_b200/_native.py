@@ -35,6 +35,7 @@ SIGNATURES = {
     "frcnn_version": (ci, []),
     "frcnn_last_error": (ci, [C.c_char_p, sz]),
     "frcnn_check_device": (ci, [ci]),
+    "frcnn_zero_async": (ci, [vp, sz, vp]),
     "frcnn_nms_host": (ci, [ip, ip, fp, ci, ci, cf, ci, cu]),
     "frcnn_nms_sorted_dev": (ci, [vp, ci, cf, cu, ci, vp, vp, vp]),
     "frcnn_conv_plan_create": (ci, [C.POINTER(vp), C.POINTER(ConvDesc)]),

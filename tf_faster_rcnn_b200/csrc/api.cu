@@ -47,3 +47,9 @@ extern "C" int frcnn_check_device(int device_id) {
   }
   return frcnn::OK;
 }
+
+extern "C" int frcnn_zero_async(void* dev_ptr, size_t bytes, void* stream) {
+  FRCNN_REQUIRE(dev_ptr, "zero_async: null pointer");
+  if (bytes) FRCNN_CUDA(cudaMemsetAsync(dev_ptr, 0, bytes, (cudaStream_t)stream));
+  return frcnn::OK;
+}

@@ -300,7 +300,7 @@ class ShapePlan:
                                                   ops._p(self.keep), ops._p(self.keep_cnt), ops._p(self.keep_score), ops._p(self.post_ws),
                                                   self.post_ws.numel(), ops._stream()), "detect_post")
             return post
-        self.recs = [torch.zeros((B, stride), dtype=torch.float32, device="cuda") for _ in range(2)]
+        self.recs = [ops.zeros((B, stride)) for _ in range(2)]
         self.post_steps = [make_post(r) for r in self.recs]
         self.post_key = key
         self._select(0)

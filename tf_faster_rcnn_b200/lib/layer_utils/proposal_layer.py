@@ -26,7 +26,7 @@ def _select(proposals, scores, pre_nms_top_n, post_nms_top_n, thresh, flags):
     order = torch.empty(n, dtype=torch.int32, device="cuda"); sk = torch.empty(n, dtype=torch.float32, device="cuda")
     ops.sort_desc(sd, order, sk)
     rois = torch.empty((post, 5), dtype=torch.float32, device="cuda"); rs = torch.empty(post, dtype=torch.float32, device="cuda")
-    keep = torch.empty(post, dtype=torch.int32, device="cuda"); num = torch.zeros(1, dtype=torch.int32, device="cuda")
+    keep = torch.empty(post, dtype=torch.int32, device="cuda"); num = torch.empty(1, dtype=torch.int32, device="cuda")
     ops.proposals(pd, sd, order, int(pre_nms_top_n), post, thresh, flags, rois, rs, keep, num)
     k = int(num.item())
     return rois[:k].cpu().numpy(), rs[:k].cpu().numpy().reshape(-1, 1)

@@ -214,7 +214,11 @@ def _test_net_sharded(imdb, detect_record, verbose=True):
             # ranks without an image (N < W) learn the record size from the others: one extra tiny collective, once
             cap = torch.tensor([rec.numel() if rec is not None else 0], dtype=torch.int64, device=device)
             dist.all_reduce(cap, op=dist.ReduceOp.MAX)
-            idle = torch.zeros(int(cap.item()), dtype=torch.float32, device=device)
+            if device.type == "cuda":
+                from tf_faster_rcnn_b200 import ops
+                idle = ops.zeros(int(cap.item()))
+            else:
+                idle = torch.zeros(int(cap.item()), dtype=torch.float32)
             gather = parallel.RecordGather(idle, world)
         gather.issue(slot, rec if rec is not None else idle)
         if step > 0:

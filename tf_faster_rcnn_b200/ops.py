@@ -24,6 +24,13 @@ def _f32(t):
     return t
 
 
+def zeros(shape, dtype=torch.float32):
+    """Device buffer cleared with cudaMemsetAsync on the current stream (no framework fill kernel on the path)."""
+    t = torch.empty(shape, dtype=dtype, device="cuda")
+    N.check(N.lib().frcnn_zero_async(_p(t), t.numel() * t.element_size(), _stream()), "zero_async")
+    return t
+
+
 def same_pads(n, k, s):
     """TF 'SAME' padding (before, after) for one dimension."""
     out = -(-n // s)
