@@ -59,6 +59,15 @@ int frcnn_check_device(int device_id);
 /* cudaMemsetAsync(dev_ptr, 0, bytes) on `stream`: lets a host layer clear buffers (detection records) without a framework fill kernel */
 int frcnn_zero_async(void* dev_ptr, size_t bytes, void* stream);
 
+/* CUDA-graph capture of a sequence of the stage calls below (one image or batch = one replay): begin on a NON-default stream,
+ * enqueue the stages on that stream, end -> an executable graph; launch it on any stream.  No allocation or synchronisation
+ * happens inside the stages, so the whole TEST-mode path is capturable. */
+typedef struct frcnn_graph frcnn_graph;
+int frcnn_graph_begin(void* stream);
+int frcnn_graph_end(void* stream, frcnn_graph** out);
+int frcnn_graph_launch(const frcnn_graph* g, void* stream);
+void frcnn_graph_destroy(frcnn_graph* g);
+
 /* ---- (1) NMS, host buffers: replaces `_nms` (lib/nms/gpu_nms.hpp:1-2, nms_kernel.cu:91-144) ----------
  * boxes_host: [boxes_num, boxes_dim>=4] rows (x1,y1,x2,y2,...), ALREADY sorted by descending score, as the
  * reference's Cython wrapper guarantees (gpu_nms.pyx:25-28).  keep_out: capacity boxes_num; receives

@@ -60,7 +60,7 @@ def test_every_entry_rejects_null_arguments_before_touching_a_device():
     from tf_faster_rcnn_b200 import _native
     L = _native.lib()
     skip = {"frcnn_version", "frcnn_last_error", "frcnn_check_device", "frcnn_sort_workspace_bytes", "frcnn_detect_post_workspace_bytes",
-            "frcnn_conv_plan_destroy"}
+            "frcnn_conv_plan_destroy", "frcnn_graph_destroy"}
     checked = 0
     for name in _native.SIGNATURES:
         if name in skip:
@@ -74,6 +74,7 @@ def test_every_entry_rejects_null_arguments_before_touching_a_device():
     assert checked >= 18
     assert L.frcnn_sort_workspace_bytes(0) >= 0
     L.frcnn_conv_plan_destroy(None)                       # destroying nothing is a no-op
+    L.frcnn_graph_destroy(None)
 
 
 def test_product_package_never_imports_the_oracle():

@@ -36,6 +36,10 @@ SIGNATURES = {
     "frcnn_last_error": (ci, [C.c_char_p, sz]),
     "frcnn_check_device": (ci, [ci]),
     "frcnn_zero_async": (ci, [vp, sz, vp]),
+    "frcnn_graph_begin": (ci, [vp]),
+    "frcnn_graph_end": (ci, [vp, C.POINTER(vp)]),
+    "frcnn_graph_launch": (ci, [vp, vp]),
+    "frcnn_graph_destroy": (None, [vp]),
     "frcnn_nms_host": (ci, [ip, ip, fp, ci, ci, cf, ci, cu]),
     "frcnn_nms_sorted_dev": (ci, [vp, ci, cf, cu, ci, vp, vp, vp]),
     "frcnn_conv_plan_create": (ci, [C.POINTER(vp), C.POINTER(ConvDesc)]),

@@ -53,3 +53,38 @@ extern "C" int frcnn_zero_async(void* dev_ptr, size_t bytes, void* stream) {
   if (bytes) FRCNN_CUDA(cudaMemsetAsync(dev_ptr, 0, bytes, (cudaStream_t)stream));
   return frcnn::OK;
 }
+
+// ---- CUDA-graph capture of a launch sequence (the host layer records its stage calls once per shape and replays them) ----------
+struct frcnn_graph { cudaGraphExec_t exec; };
+
+extern "C" int frcnn_graph_begin(void* stream) {
+  FRCNN_REQUIRE(stream, "graph_begin: capture needs a non-default stream");
+  FRCNN_CUDA(cudaStreamBeginCapture((cudaStream_t)stream, cudaStreamCaptureModeThreadLocal));
+  return frcnn::OK;
+}
+
+extern "C" int frcnn_graph_end(void* stream, frcnn_graph** out) {
+  FRCNN_REQUIRE(stream && out, "graph_end: null argument");
+  *out = nullptr;
+  cudaGraph_t g = nullptr;
+  FRCNN_CUDA(cudaStreamEndCapture((cudaStream_t)stream, &g));
+  cudaGraphExec_t exec = nullptr;
+  cudaError_t e = cudaGraphInstantiate(&exec, g, 0);
+  cudaGraphDestroy(g);
+  if (e != cudaSuccess) return frcnn::cuda_fail(e, "cudaGraphInstantiate", __FILE__, __LINE__);
+  frcnn_graph* h = new frcnn_graph{exec};
+  *out = h;
+  return frcnn::OK;
+}
+
+extern "C" int frcnn_graph_launch(const frcnn_graph* g, void* stream) {
+  FRCNN_REQUIRE(g && g->exec, "graph_launch: null graph");
+  FRCNN_CUDA(cudaGraphLaunch(g->exec, (cudaStream_t)stream));
+  return frcnn::OK;
+}
+
+extern "C" void frcnn_graph_destroy(frcnn_graph* g) {
+  if (!g) return;
+  if (g->exec) cudaGraphExecDestroy(g->exec);
+  delete g;
+}

@@ -10,6 +10,7 @@ backbones emit their layers through the Tape from lib/nets/{vgg16,resnet_v1,mobi
 counterparts in tf_faster_rcnn_b200/lib/nets/.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -66,6 +67,47 @@ class Weights:
             w, sc, sh = build()
             self._packed[key] = ops.PackedConv(w, sc, sh)
         return self._packed[key]
+
+
+class LaunchGraph:
+    """A recorded launch sequence as an executable CUDA graph, captured and replayed through the C ABI (frcnn_graph_*): plain
+    cudaStreamBeginCapture / cudaGraphLaunch on the stream the stages were enqueued on -- no framework graph object, no
+    generator-state fill kernels per replay.  FRCNN_TORCH_GRAPH=1 selects torch.cuda.CUDAGraph instead (A/B, debugging)."""
+
+    def __init__(self, fns):
+        self._h = ctypes.c_void_p()
+        self._torch = None
+        if os.environ.get("FRCNN_TORCH_GRAPH") == "1":
+            self._torch = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._torch):
+                for fn in fns:
+                    fn()
+            return
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            N.check(N.lib().frcnn_graph_begin(C_void(side.cuda_stream)), "graph_begin")
+            try:
+                for fn in fns:
+                    fn()
+            finally:
+                rc = N.lib().frcnn_graph_end(C_void(side.cuda_stream), ctypes.byref(self._h))
+            N.check(rc, "graph_end")
+        torch.cuda.current_stream().wait_stream(side)
+
+    def replay(self):
+        if self._torch is not None:
+            self._torch.replay()
+        else:
+            N.check(N.lib().frcnn_graph_launch(self._h, ops._stream()), "graph_launch")
+
+    def __del__(self):
+        try:
+            if self._h:
+                N.lib().frcnn_graph_destroy(self._h)
+                self._h = ctypes.c_void_p()
+        except Exception:
+            pass
 
 
 class Tape:
@@ -350,10 +392,7 @@ class ShapePlan:
                 for fn in fns:                        # warm-up: function attributes, lazy allocations
                     fn()
                 torch.cuda.current_stream().synchronize()
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    for fn in fns:
-                        fn()
+                g = LaunchGraph(fns)
                 self.graphs[gkey] = g
             g.replay()
         else:
