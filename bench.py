@@ -364,6 +364,25 @@ def run_ours(args):
     if sampler:
         sampler.stop_flag = True
         sampler.join(timeout=2)
+    # the reference's own batch size beside the headline: the same image stream one image per graph replay (1 GPU only; untimed
+    # by the contract -- reported so that both operating points come out of the same run)
+    batch1 = None
+    if world == 1 and B != 1 and not args.no_batch1:
+        p1 = net.plan_for(H, W, 1)
+        p1.image.copy_(host_blob[:1])
+        for _ in range(3):
+            p1.launch(post=True, detect=True)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n1 = max(args.steps, 20)
+        e0.record()
+        for _ in range(n1):
+            p1.launch(post=True, detect=True)
+        e1.record()
+        torch.cuda.synchronize()
+        ms1 = e0.elapsed_time(e1) / n1
+        batch1 = {"value": 1000.0 / ms1, "unit": "images/s", "ms_per_image": ms1, "steps": n1,
+                  "note": "device-resident, one image per graph replay (the reference's batch size)"}
     # context for the roofline: what the tensor cores of THIS board give a plain library GEMM right now (burst, 8192^3)
     lib_peaks = {}
     if rank == 0 and not args.no_lib_peaks:
@@ -415,6 +434,7 @@ def run_ours(args):
         "e2e": {"value": e2e_v, "unit": "images/s", "h2d_bytes_per_step": int(host_blob.numel() * 4 + B * 12), "d2h_bytes_per_step": int(rec_bytes),
                 "ms_per_step": ms_e2e / n_steps, "api": "Network.submit_batch(pinned host blobs) / collect_batch() -> per-image detection records on the host, two batches in flight"},
         "gpu_launches": launches_per_step * n_steps,
+        "batch1": batch1,
         "clocks": sampler.summary() if sampler else None,
         "roofline": {"bound": "tensor", "kernel": "conv_gemm_f16x3_kernel (all %d conv/FC launches of one step of %d image(s))" % (len(conv_steps), B),
                      "achieved": conv_tflops, "peak": peak, "unit": "TFLOP/s", "frac": conv_tflops / peak, "traffic": traffic,
@@ -452,6 +472,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--net", default="res101", choices=sorted(NETS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-batch1", action="store_true", help="skip the extra batch-1 measurement reported beside the headline")
     ap.add_argument("--no-lib-peaks", action="store_true", help="skip the two 8192^3 library matmuls timed for context after the run")
     ap.add_argument("--precision", default="fp32-grade", choices=["fp32-grade", "f16x1"],
                     help="f16x1 = the opt-in THROUGHPUT mode (plain fp16 operands, fp32 accumulate): NOT the parity path, its line says so")
